@@ -1,0 +1,146 @@
+/* pam.h -- C ABI of libpam.so, the B200 (sm_100a) implementation of the per-frame geometric hot
+ * path of Part-Aware Measurement (cross-view association, part-aware view filtering, weighted DLT
+ * triangulation, track life-cycle).
+ *
+ * The reference has no FFI: its boundary is a set of plain Python functions / classes
+ * (SURVEY.md section 8b).  Each entry point below names the reference interface it replaces
+ * (paths relative to /root/reference/src); INTEGRATION.md shows the ctypes binding a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = PAM_OK, negative = pam_status error
+ *   - no exceptions / aborts cross the ABI; pam_last_error(h) gives a message
+ *   - "d_" arguments are DEVICE pointers owned by the caller, "h_" arguments are HOST pointers;
+ *     the library never frees caller memory
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); "d_" entry points are
+ *     asynchronous on that stream, "h_"/"_host" entry points synchronise before returning
+ *   - one handle per (device, host thread)
+ *   - 2-D detections are (v, u, conf) = (row, col, confidence) triples like the reference's
+ *     (ivclabpose.py:238-244); 3-D joints are (x, y, z) in world units
+ */
+#ifndef PAM_H
+#define PAM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAM_ABI_VERSION 1
+
+/* compile-time capacity limits of the stateful tracker (pam_core.h) */
+#define PAM_LIMIT_CAMERAS 8
+#define PAM_LIMIT_TRACKS 16
+#define PAM_LIMIT_DETECTIONS 16
+#define PAM_LIMIT_JOINTS 32
+
+typedef enum pam_status {
+    PAM_OK = 0,
+    PAM_E_INVALID = -1,        /* bad argument / configuration outside the limits above          */
+    PAM_E_CUDA = -2,           /* a CUDA runtime call failed (no device, out of memory, ...)      */
+    PAM_E_NOCAMERAS = -3,      /* pam_set_cameras has not been called                              */
+    PAM_E_CAPACITY = -4,       /* a sequence exceeded max_tracks / hypotheses / max_detections     */
+    PAM_E_INTERNAL = -5
+} pam_status;
+
+/* Tracker hyper-parameters = the fields ivclabpose copies into iter_args (ivclabpose.py:140-156)
+ * that live code reads, plus the constants the reference hard-wires. */
+typedef struct pam_config {
+    int32_t num_cameras;        /* V                                                              */
+    int32_t num_joints;         /* J   (reference: 17 hard-wired)                                  */
+    int32_t max_detections;     /* D   stride of the detection tensors                             */
+    int32_t max_tracks;         /* track slots per sequence = stride of the output tensors        */
+    int32_t n_init;             /* N_INIT   tracking/IterativeTracker.py:259                       */
+    int32_t max_age;            /* MAX_AGE  :273, :331                                             */
+    int32_t min_valid_joints;   /* the "> 10" of :145                                              */
+    int32_t stale_window;       /* the "<= 3" of :317                                              */
+    uint32_t arm_joint_mask;    /* bit j set: joint j is smoothed with arm_sigma (":382" [9,10])   */
+    uint32_t reserved0;
+    double conf_threshold;      /* CONF_THRESHOLD  :59                                             */
+    double epi_threshold;       /* EPI_THRESHOLD   tracking/hypothesis.py:63                       */
+    double init_threshold;      /* INIT_THRESHOLD  tracking/hypothesis.py:32                       */
+    double joint_threshold;     /* JOINT_THRESHOLD :346                                            */
+    double alpha2d;             /* ALPHA2D  :143                                                   */
+    double lambda_a;            /* LAMBDA_A :148                                                   */
+    double lambda_t;            /* LAMBDA_T utils/construction.py:96                               */
+    double sigma;               /* SIGMA     :381                                                  */
+    double arm_sigma;           /* ARM_SIGMA :382                                                  */
+    double veto_believe;        /* the "> 0.5" of tracking/hypothesis.py:66                        */
+} pam_config;
+
+/* Byte layout of one sequence's tracker state inside the caller's state buffer, so that host
+ * code can read tracks back (IterTrack read surface, tracking/IterativeTracker.py:194-204). */
+typedef struct pam_state_layout {
+    int64_t seq_bytes;          /* stride between sequences                                         */
+    int64_t off_header;         /* int32: ntracks, next_id, status, frames_done, used_mask, order[16] */
+    int64_t off_meta;           /* per slot, int32 x meta_ints                                      */
+    int64_t off_hist;           /* double [slot][hist_len][J][3]  smoothed pose ring                */
+    int64_t off_view;           /* float  [slot][V][J][3]         last (v,u,conf) per view slot     */
+    int64_t off_vel;            /* float  [slot][J][3]            velocity                          */
+    int64_t off_nviews;         /* uint8  [slot][J]               views used for the last pose      */
+    int32_t meta_ints;          /* ints per slot: id,hits,age,tsu,state,already,nviews,hist_start,
+                                   hist_len, view_cid[8], view_time[8], hist_time[hist_ring]       */
+    int32_t hist_ring;          /* ring length                                                      */
+    int32_t max_views;          /* 8                                                                */
+    int32_t max_order;          /* 16                                                               */
+} pam_state_layout;
+
+typedef struct pam_handle pam_handle;
+
+int pam_abi_version(void);
+const char* pam_status_string(int status);
+const char* pam_last_error(const pam_handle* h);
+
+/* IterativeTracker.__init__ (tracking/IterativeTracker.py:36-45): validate + freeze parameters. */
+int pam_create(const pam_config* cfg, int device, pam_handle** out);
+int pam_destroy(pam_handle* h);
+
+/* Camera constants of ivclabpose.GetCameraParameters / Camera.__init__ (ivclabpose.py:35-46,
+ * 162-181), HOST pointers, copied to the device: P [V][3][4] f32, RKinv [V][3][3] f32,
+ * position [V][3] f64, F [V][V][3][3] f32 with F[a][b] = cameras[a].F[b]. */
+int pam_set_cameras(pam_handle* h, const float* h_P, const float* h_RKinv, const double* h_position,
+                    const float* h_F);
+
+/* ---- stateful path: IterativeTracker.tracking (tracking/IterativeTracker.py:115-180) ---------- */
+
+int pam_get_state_layout(const pam_handle* h, pam_state_layout* out);
+
+/* track_restart (tracking/IterativeTracker.py:47-50) for S sequences: d_state = S * seq_bytes. */
+int pam_track_reset(pam_handle* h, void* d_state, int32_t S, void* stream);
+
+/* Run T consecutive frames (frame ids frame0 .. frame0+T-1) of S independent sequences, one CTA
+ * per sequence, no host involvement between frames.
+ *   d_dets   [S][T][V][D][J][3] f32 (v,u,conf), zero padded        d_counts [S][T][V] i32
+ *   d_out_count [S][T] i32   number of reported tracks (Confirmed and updated this frame,
+ *                            ivclabpose.py:265-267), in track-list order
+ *   d_out_ids   [S][T][max_tracks] i32          d_out_joints [S][T][max_tracks][J][3] f32
+ *   d_out_nviews [S][T][max_tracks][J] u8 (may be NULL)  views each joint was built from
+ *   d_out_assoc  [S][T][V][D] i32 (may be NULL) track id matched to each detection, -1 = none */
+int pam_track_sequences(pam_handle* h, void* d_state, int32_t S, int32_t T, int32_t frame0,
+                        const float* d_dets, const int32_t* d_counts, int32_t* d_out_count,
+                        int32_t* d_out_ids, float* d_out_joints, uint8_t* d_out_nviews,
+                        int32_t* d_out_assoc, void* stream);
+
+/* Per-sequence status words (0 = ok, >0 = capacity error code); synchronises `stream`.
+ * Returns PAM_E_CAPACITY if any sequence is in error. */
+int pam_track_status(pam_handle* h, const void* d_state, int32_t S, int32_t* h_status, void* stream);
+
+/* Same as pam_track_sequences with HOST buffers: allocates/reuses device workspace inside the
+ * handle, copies in, runs, copies out, synchronises.  `fresh` != 0 restarts the trackers first. */
+int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0, int32_t fresh,
+                             const float* h_dets, const int32_t* h_counts, int32_t* h_out_count,
+                             int32_t* h_out_ids, float* h_out_joints, uint8_t* h_out_nviews,
+                             int32_t* h_out_assoc);
+
+/* Copy the internal state of the _host path (S sequences) to a host buffer of S*seq_bytes. */
+int pam_track_state_to_host(pam_handle* h, int32_t S, void* h_state);
+
+/* number of kernel launches issued through this handle so far (bench.py "gpu_launches") */
+int64_t pam_launch_count(const pam_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAM_H */

@@ -1,0 +1,368 @@
+// pam_core.h -- per-item numerics of the part-aware measurement path (host/device inline).
+//
+// Every function here is the arithmetic ONE thread performs for ONE work item (a joint, a view
+// pair, a track/detection pair, one assignment problem).  The file is plain C++ so that the
+// very same source is compiled by nvcc into the sm_100a kernels (pam_kernels.cu) and by g++
+// into the host-side debugging harness under tests/hostemu/ (never shipped, never loaded by
+// the package).
+//
+// Reference semantics followed (paths under /root/reference/src):
+//   np_sum / np_mean            numpy add.reduce order (pairwise_sum in numpy/_core/src/umath/loops_utils.h.src)
+//   epi_line_* / epi_dist_*     utils/matching.py:115-151 (float64 form), :50-91 + cv::computeCorrespondEpilines
+//   ray_point_distance          utils/matching.py:10-17 + utils/calculate.py:26-32
+//   greedy_update / greedy_init utils/matching.py:243-295
+//   dlt_*                       utils/construction.py:89-114  (rows, weights; the SVD is replaced by
+//                               a streaming Givens QR + one-sided Jacobi SVD of the 4x4 factor)
+//   lsap_solve                  scipy.optimize.linear_sum_assignment (rectangular_lsap.cpp, Crouse 2016)
+//   reflect_index / gauss_last  scipy.ndimage.gaussian_filter1d(mode='reflect') last output sample,
+//                               tracking/IterativeTracker.py:371-383
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PAM_HD __host__ __device__ __forceinline__
+#define PAM_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define PAM_HD inline
+#define PAM_HD_NOINLINE
+#endif
+
+#define PAM_MAX_V 8        // cameras per rig handled by the stateful tracker
+#define PAM_MAX_TRK 16     // track slots per sequence
+#define PAM_MAX_D 16       // detections per camera per frame
+#define PAM_MAX_J 32       // joints
+#define PAM_MAX_HYP 32     // person hypotheses during new-track initialisation
+#define PAM_HIST 12        // smoothed-pose history ring (max_age + 2 <= PAM_HIST)
+#define PAM_MAX_RADIUS 8   // Gaussian radius int(4 sigma + 0.5)
+#define PAM_MAX_AGEW 8     // stale-view window + 1
+
+namespace pam {
+
+// ------------------------------------------------------------------------------------------
+// numpy reduction order
+// ------------------------------------------------------------------------------------------
+// n <= 128: the non-recursive leaf of numpy's pairwise_sum (all on-device reductions: J <= 32, V <= 31)
+template <class T>
+PAM_HD T np_sum(const T* a, int n, int stride = 1) {
+    if (n < 8) {
+        T r = (T)0;
+        for (int i = 0; i < n; ++i) r += a[i * stride];
+        return r;
+    }
+    T r0 = a[0], r1 = a[stride], r2 = a[2 * stride], r3 = a[3 * stride];
+    T r4 = a[4 * stride], r5 = a[5 * stride], r6 = a[6 * stride], r7 = a[7 * stride];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+        r0 += a[(i + 0) * stride]; r1 += a[(i + 1) * stride];
+        r2 += a[(i + 2) * stride]; r3 += a[(i + 3) * stride];
+        r4 += a[(i + 4) * stride]; r5 += a[(i + 5) * stride];
+        r6 += a[(i + 6) * stride]; r7 += a[(i + 7) * stride];
+    }
+    T res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; ++i) res += a[i * stride];
+    return res;
+}
+
+// running 8-lane accumulator reproducing np_sum for a stream of n <= 128 values whose count is
+// known up front (used where the addends are produced on the fly and never stored)
+template <class T>
+struct NpSumStream {
+    T r[8];
+    T res;
+    int n, i, nblk;
+    PAM_HD void begin(int count) {
+        n = count; i = 0; nblk = count - (count % 8); res = (T)0;
+        for (int k = 0; k < 8; ++k) r[k] = (T)0;
+    }
+    PAM_HD void push(T x) {
+        if (n < 8) { res += x; }
+        else if (i < nblk) {
+            int k = i & 7;
+            if (i < 8) r[k] = x; else r[k] += x;
+            if (i == nblk - 1) res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        } else { res += x; }
+        ++i;
+    }
+    PAM_HD T total() const { return res; }
+};
+
+// ------------------------------------------------------------------------------------------
+// epipolar geometry
+// ------------------------------------------------------------------------------------------
+// F is the 3x3 (row-major) fundamental matrix cams[a].F[cid_b]:  x_a^T F x_b = 0,  x = (u, v, 1).
+
+// float64 form of utils/matching.py:136-146: line l = F^T x_a in image b, normalised by
+// ||l[:2]|| (0 -> 1), distance |l . x_b| / sqrt(l0^2 + l1^2).
+PAM_HD double epi_dist_f64(const double* F, double ua, double va, double ub, double vb) {
+    double l0 = F[0] * ua + F[3] * va + F[6];
+    double l1 = F[1] * ua + F[4] * va + F[7];
+    double l2 = F[2] * ua + F[5] * va + F[8];
+    double nu = sqrt(l0 * l0 + l1 * l1);
+    if (nu == 0.0) nu = 1.0;
+    l0 /= nu; l1 /= nu; l2 /= nu;
+    double nn = l0 * l0 + l1 * l1;
+    if (nn == 0.0) nn = 1.0;
+    return fabs(ub * l0 + vb * l1 + l2) / sqrt(nn);
+}
+
+// same with the transposed matrix: line l = F x_b in image a, distance of x_a to it
+PAM_HD double epi_dist_f64_T(const double* F, double ub, double vb, double ua, double va) {
+    double l0 = F[0] * ub + F[1] * vb + F[2];
+    double l1 = F[3] * ub + F[4] * vb + F[5];
+    double l2 = F[6] * ub + F[7] * vb + F[8];
+    double nu = sqrt(l0 * l0 + l1 * l1);
+    if (nu == 0.0) nu = 1.0;
+    l0 /= nu; l1 /= nu; l2 /= nu;
+    double nn = l0 * l0 + l1 * l1;
+    if (nn == 0.0) nn = 1.0;
+    return fabs(ua * l0 + va * l1 + l2) / sqrt(nn);
+}
+
+// cv::computeCorrespondEpilines arithmetic (double path): (a,b,c) = M x, nu = a^2+b^2,
+// nu = nu ? 1/sqrt(nu) : 1, scaled;  then utils/matching.py:82-83:
+// |x . l| / sqrt(l0^2 + l1^2).   transposed = false: M = F ;  true: M = F^T.
+PAM_HD double epi_dist_cv(const double* F, bool transposed, double xs, double ys, double xt, double yt) {
+    double a, b, c;
+    if (!transposed) {
+        a = F[0] * xs + F[1] * ys + F[2];
+        b = F[3] * xs + F[4] * ys + F[5];
+        c = F[6] * xs + F[7] * ys + F[8];
+    } else {
+        a = F[0] * xs + F[3] * ys + F[6];
+        b = F[1] * xs + F[4] * ys + F[7];
+        c = F[2] * xs + F[5] * ys + F[8];
+    }
+    double nu = a * a + b * b;
+    nu = (nu != 0.0) ? 1.0 / sqrt(nu) : 1.0;
+    a *= nu; b *= nu; c *= nu;
+    return fabs(xt * a + yt * b + c) / sqrt(a * a + b * b);
+}
+
+// epipolar_distance(cam1, person1, cam2, person2)[j] = [d1, d2] with F = cam1.F[cam2.cid]:
+//   d1 = distance of x1 to the line F x2 (in image 1), d2 = distance of x2 to F^T x1 (in image 2).
+PAM_HD void epi_pair_cv(const double* F12, double u1, double v1, double u2, double v2, double& d1, double& d2) {
+    d1 = epi_dist_cv(F12, false, u2, v2, u1, v1);
+    d2 = epi_dist_cv(F12, true, u1, v1, u2, v2);
+}
+
+// ------------------------------------------------------------------------------------------
+// back-projected ray to 3-D point distance
+// ------------------------------------------------------------------------------------------
+// RK = R^-1 K^-1 (row-major 3x3), pos = camera centre, (u, v) pixel, X = 3-D point.
+PAM_HD double ray_point_distance(const double* RK, const double* pos, double u, double v, const double* X) {
+    double d0 = RK[0] * u + RK[1] * v + RK[2];
+    double d1 = RK[3] * u + RK[4] * v + RK[5];
+    double d2 = RK[6] * u + RK[7] * v + RK[8];
+    double nrm = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    d0 /= nrm; d1 /= nrm; d2 /= nrm;
+    // x2 - x1 with x2 = pos + dir, as the reference forms it (utils/calculate.py:29-30)
+    double a0 = (pos[0] + d0) - pos[0], a1 = (pos[1] + d1) - pos[1], a2 = (pos[2] + d2) - pos[2];
+    double b0 = pos[0] - X[0], b1 = pos[1] - X[1], b2 = pos[2] - X[2];
+    double c0 = a1 * b2 - a2 * b1;
+    double c1 = a2 * b0 - a0 * b2;
+    double c2 = a0 * b1 - a1 * b0;
+    return sqrt(c0 * c0 + c1 * c1 + c2 * c2) / sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+}
+
+// ------------------------------------------------------------------------------------------
+// triangulation: weighted homogeneous DLT
+// ------------------------------------------------------------------------------------------
+// Upper-triangular 4x4 factor R (10 entries) of the stacked rows, built row by row with Givens
+// rotations, so the system never has to exist in memory whatever the number of views.
+struct DltAccum {
+    double r00, r01, r02, r03, r11, r12, r13, r22, r23, r33;
+    PAM_HD void reset() { r00 = r01 = r02 = r03 = r11 = r12 = r13 = r22 = r23 = r33 = 0.0; }
+
+    PAM_HD static void givens(double& d, double& x, double& c, double& s) {
+        // rotate (d, x) -> (r, 0); c, s from a reciprocal square root
+        double h2 = d * d + x * x;
+        double inv = 1.0 / sqrt(h2);
+        c = d * inv; s = x * inv;
+        d = h2 * inv; x = 0.0;
+    }
+    PAM_HD void add_row(double x0, double x1, double x2, double x3) {
+        double c, s, t;
+        if (x0 != 0.0) {
+            givens(r00, x0, c, s);
+            t = r01; r01 = c * t + s * x1; x1 = c * x1 - s * t;
+            t = r02; r02 = c * t + s * x2; x2 = c * x2 - s * t;
+            t = r03; r03 = c * t + s * x3; x3 = c * x3 - s * t;
+        }
+        if (x1 != 0.0) {
+            givens(r11, x1, c, s);
+            t = r12; r12 = c * t + s * x2; x2 = c * x2 - s * t;
+            t = r13; r13 = c * t + s * x3; x3 = c * x3 - s * t;
+        }
+        if (x2 != 0.0) {
+            givens(r22, x2, c, s);
+            t = r23; r23 = c * t + s * x3; x3 = c * x3 - s * t;
+        }
+        if (x3 != 0.0) {
+            givens(r33, x3, c, s);
+        }
+    }
+    // the two DLT rows of one view (utils/construction.py:92-97):
+    //   (u P2 - P0)/||.|| * w ,  (v P2 - P1)/||.|| * w      with P row-major 3x4
+    PAM_HD void add_view(const double* P, double u, double v, double w) {
+        double a0 = u * P[8] - P[0], a1 = u * P[9] - P[1], a2 = u * P[10] - P[2], a3 = u * P[11] - P[3];
+        double na = sqrt(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3);
+        add_row(a0 / na * w, a1 / na * w, a2 / na * w, a3 / na * w);
+        double b0 = v * P[8] - P[4], b1 = v * P[9] - P[5], b2 = v * P[10] - P[6], b3 = v * P[11] - P[7];
+        double nb = sqrt(b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3);
+        add_row(b0 / nb * w, b1 / nb * w, b2 / nb * w, b3 / nb * w);
+    }
+
+    // Right singular vector of the smallest singular value by one-sided (Hestenes) Jacobi on
+    // the columns of R; de-homogenised into X[3].  Replaces la.svd at utils/construction.py:110-113.
+    PAM_HD void solve(double* X) const {
+        double g[4][4] = {{r00, r01, r02, r03}, {0.0, r11, r12, r13}, {0.0, 0.0, r22, r23}, {0.0, 0.0, 0.0, r33}};
+        double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+        for (int sweep = 0; sweep < 12; ++sweep) {
+            bool rotated = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int p = 0; p < 3; ++p) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int q = p + 1; q < 4; ++q) {
+                    double al = 0.0, be = 0.0, ga = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (int k = 0; k < 4; ++k) {
+                        al += g[k][p] * g[k][p];
+                        be += g[k][q] * g[k][q];
+                        ga += g[k][p] * g[k][q];
+                    }
+                    if (ga == 0.0 || fabs(ga) <= 1e-17 * sqrt(al * be)) continue;
+                    rotated = true;
+                    double zeta = (be - al) / (2.0 * ga);
+                    double t = 1.0 / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    if (zeta < 0.0) t = -t;
+                    double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (int k = 0; k < 4; ++k) {
+                        double gp = g[k][p], gq = g[k][q];
+                        g[k][p] = c * gp - s * gq;
+                        g[k][q] = s * gp + c * gq;
+                        double vp = V[k][p], vq = V[k][q];
+                        V[k][p] = c * vp - s * vq;
+                        V[k][q] = s * vp + c * vq;
+                    }
+                }
+            }
+            if (!rotated) break;
+        }
+        double best = 0.0;
+        int arg = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < 4; ++q) {
+            double nq = g[0][q] * g[0][q] + g[1][q] * g[1][q] + g[2][q] * g[2][q] + g[3][q] * g[3][q];
+            if (q == 0 || nq < best) { best = nq; arg = q; }
+        }
+        double x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < 4; ++q)
+            if (q == arg) { x0 = V[0][q]; x1 = V[1][q]; x2 = V[2][q]; x3 = V[3][q]; }
+        X[0] = x0 / x3; X[1] = x1 / x3; X[2] = x2 / x3;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// rectangular linear sum assignment (scipy rectangular_lsap.cpp / Crouse 2016)
+// ------------------------------------------------------------------------------------------
+// cost(i, j) for i < nr, j < nc (minimised).  col4row[i] = assigned column or -1.  When nc < nr
+// the transposed problem is solved, exactly as scipy does.  Returns 0, or -1 if infeasible.
+template <int MAXN, class CostFn>
+PAM_HD_NOINLINE int lsap_solve(int nr0, int nc0, CostFn cost, int* col4row_out) {
+    for (int i = 0; i < nr0; ++i) col4row_out[i] = -1;
+    if (nr0 == 0 || nc0 == 0) return 0;
+    const bool transpose = nc0 < nr0;
+    const int nr = transpose ? nc0 : nr0, nc = transpose ? nr0 : nc0;
+    double u[MAXN], v[MAXN], sp[MAXN];
+    int path[MAXN], col4row[MAXN], row4col[MAXN], remaining[MAXN];
+    uint32_t SR, SC;
+    for (int i = 0; i < nr; ++i) { u[i] = 0.0; col4row[i] = -1; }
+    for (int j = 0; j < nc; ++j) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
+    const double INF = HUGE_VAL;
+    for (int cur = 0; cur < nr; ++cur) {
+        double minVal = 0.0;
+        int i = cur;
+        int num_remaining = nc;
+        for (int it = 0; it < nc; ++it) { remaining[it] = nc - it - 1; sp[it] = INF; }
+        SR = 0u; SC = 0u;
+        int sink = -1;
+        while (sink == -1) {
+            int index = -1;
+            double lowest = INF;
+            SR |= (1u << i);
+            for (int it = 0; it < num_remaining; ++it) {
+                int j = remaining[it];
+                double cij = transpose ? cost(j, i) : cost(i, j);
+                double r = minVal + cij - u[i] - v[j];
+                if (r < sp[j]) { path[j] = i; sp[j] = r; }
+                if (sp[j] < lowest || (sp[j] == lowest && row4col[j] == -1)) { lowest = sp[j]; index = it; }
+            }
+            minVal = lowest;
+            if (minVal == INF) return -1;
+            int j = remaining[index];
+            if (row4col[j] == -1) sink = j; else i = row4col[j];
+            SC |= (1u << j);
+            remaining[index] = remaining[--num_remaining];
+        }
+        u[cur] += minVal;
+        for (int k = 0; k < nr; ++k)
+            if (((SR >> k) & 1u) && k != cur) u[k] += minVal - sp[col4row[k]];
+        for (int j = 0; j < nc; ++j)
+            if ((SC >> j) & 1u) v[j] -= minVal - sp[j];
+        int j = sink;
+        while (true) {
+            int k = path[j];
+            row4col[j] = k;
+            int tmp = col4row[k]; col4row[k] = j; j = tmp;
+            if (k == cur) break;
+        }
+    }
+    if (!transpose) {
+        for (int i = 0; i < nr; ++i) col4row_out[i] = col4row[i];
+    } else {
+        // col4row maps (original column) -> (original row)
+        for (int c = 0; c < nr; ++c) col4row_out[col4row[c]] = c;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// temporal smoothing
+// ------------------------------------------------------------------------------------------
+// scipy 'reflect' (half-sample symmetric) extension: d c b a | a b c d | d c b a
+PAM_HD int reflect_index(int i, int n) {
+    int p = 2 * n;
+    i %= p;
+    if (i < 0) i += p;
+    return (i < n) ? i : (p - 1 - i);
+}
+
+// Gaussian weights of scipy.ndimage._gaussian_kernel1d, order 0: w[k] for |offset| = k.
+inline int gaussian_weights(double sigma, double* w /* PAM_MAX_RADIUS+1 */) {
+    int radius = (int)(4.0 * sigma + 0.5);
+    if (radius > PAM_MAX_RADIUS) return -1;
+    double phi[2 * PAM_MAX_RADIUS + 1];
+    double sigma2 = sigma * sigma;
+    for (int x = -radius; x <= radius; ++x) phi[x + radius] = exp(-0.5 / sigma2 * (double)(x * x));
+    // numpy pairwise order for phi.sum()
+    double s = np_sum(phi, 2 * radius + 1);
+    for (int k = 0; k <= radius; ++k) w[k] = phi[radius + k] / s;
+    return radius;
+}
+
+}  // namespace pam

@@ -1,0 +1,316 @@
+// pam_lib.cu -- sm_100a kernels + the C ABI of libpam.so (include/pam.h).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+//        (see __graft_entry__.build()).  No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "pam_host.h"
+#include "pam_ops.cuh"
+
+using namespace pam;
+
+// ----------------------------------------------------------------------------------------------
+// persistent per-sequence tracker kernel: one CTA owns one sequence for all T frames
+// ----------------------------------------------------------------------------------------------
+struct DeviceCtx {
+    __host__ __device__ __forceinline__ int tid() const {
+#ifdef __CUDA_ARCH__
+        return threadIdx.x;
+#else
+        return 0;
+#endif
+    }
+    __host__ __device__ __forceinline__ int nthreads() const {
+#ifdef __CUDA_ARCH__
+        return blockDim.x;
+#else
+        return 1;
+#endif
+    }
+    __host__ __device__ __forceinline__ void sync() const {
+#ifdef __CUDA_ARCH__
+        __syncthreads();
+#endif
+    }
+};
+
+struct TrackIO {
+    const float* dets;      // [S][T][V][D][J][3]
+    const int* counts;      // [S][T][V]
+    int* out_count;         // [S][T]
+    int* out_ids;           // [S][T][MT]
+    float* out_joints;      // [S][T][MT][J][3]
+    unsigned char* out_nv;  // [S][T][MT][J]
+    int* out_assoc;         // [S][T][V][D]
+};
+
+#define PAM_TRACK_THREADS_MAX 256
+
+__global__ void __launch_bounds__(PAM_TRACK_THREADS_MAX)
+k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, int T, int frame0, const TrackIO io) {
+    extern __shared__ double arena[];
+    __shared__ SeqShared sh;
+    DeviceCtx ctx;
+    const int s = blockIdx.x;
+    SeqGlobal g;
+    g.bind(c, state + (int64_t)s * c.seq_bytes);
+    if (threadIdx.x == 0) carve(c, sh, arena);
+    load_cameras(ctx, c, sh, cc);
+    load_state(ctx, c, sh, g);
+    __syncthreads();
+    const int64_t fstride = (int64_t)c.V * c.D * c.J * 3;
+    for (int t = 0; t < T; ++t) {
+        const int64_t ft = (int64_t)s * T + t;
+        FrameOut o;
+        o.count = io.out_count ? io.out_count + ft : nullptr;
+        o.ids = io.out_ids ? io.out_ids + ft * c.max_trk : nullptr;
+        o.joints = io.out_joints ? io.out_joints + ft * c.max_trk * c.J * 3 : nullptr;
+        o.nviews = io.out_nv ? io.out_nv + ft * c.max_trk * c.J : nullptr;
+        o.assoc = io.out_assoc ? io.out_assoc + ft * c.V * c.D : nullptr;
+        frame_step(ctx, c, sh, g, frame0 + t, io.dets + ft * fstride, io.counts + ft * c.V, o);
+    }
+    store_state(ctx, c, sh, g);
+}
+
+// ----------------------------------------------------------------------------------------------
+// handle
+// ----------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct pam_handle {
+    pam_config cfg;
+    DevCfg dc;
+    int device = 0;
+    bool have_cameras = false;
+    int track_threads = 128;
+    DevBuf cam;              // packed camera constants
+    CamConst cc{};
+    // workspace of the *_host entry points
+    DevBuf ws_state, ws_dets, ws_counts, ws_count, ws_ids, ws_joints, ws_nv, ws_assoc;
+    int ws_S = 0;
+    cudaStream_t ws_stream = nullptr;
+    int64_t launches = 0;
+    std::string err;
+};
+
+static thread_local std::string g_err;
+
+static int fail(pam_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    g_err = msg;
+    return code;
+}
+static int cuda_fail(pam_handle* h, cudaError_t e, const char* what) {
+    return fail(h, PAM_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) return cuda_fail(h, _e, #call);     \
+    } while (0)
+
+extern "C" {
+
+int pam_abi_version(void) { return PAM_ABI_VERSION; }
+
+const char* pam_status_string(int s) {
+    switch (s) {
+        case PAM_OK: return "ok";
+        case PAM_E_INVALID: return "invalid argument or configuration";
+        case PAM_E_CUDA: return "CUDA runtime error";
+        case PAM_E_NOCAMERAS: return "pam_set_cameras has not been called";
+        case PAM_E_CAPACITY: return "a sequence exceeded a capacity limit (tracks / hypotheses / detections)";
+        case PAM_E_INTERNAL: return "internal error";
+        default: return "unknown status";
+    }
+}
+
+const char* pam_last_error(const pam_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int pam_create(const pam_config* cfg, int device, pam_handle** out) {
+    if (!cfg || !out) return fail(nullptr, PAM_E_INVALID, "null argument");
+    *out = nullptr;
+    pam_handle* h = new (std::nothrow) pam_handle();
+    if (!h) return fail(nullptr, PAM_E_INTERNAL, "out of host memory");
+    h->cfg = *cfg;
+    h->device = device;
+    std::string err;
+    int rc = make_devcfg(*cfg, h->dc, err);
+    if (rc != PAM_OK) { delete h; return fail(nullptr, rc, err); }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        delete h;
+        return fail(nullptr, PAM_E_CUDA, std::string("no usable CUDA device (libpam has no CPU fallback): ") +
+                                             (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range"));
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaSetDevice"); }
+    const char* nt = getenv("PAM_TRACK_THREADS");
+    if (nt) {
+        int v = atoi(nt);
+        if (v >= 32 && v <= PAM_TRACK_THREADS_MAX) h->track_threads = (v / 32) * 32;
+    } else {
+        int want = cfg->max_tracks * cfg->num_joints;     // one thread per (track, joint)
+        h->track_threads = want <= 64 ? 64 : (want <= 128 ? 128 : (want <= 192 ? 192 : 256));
+    }
+    *out = h;
+    return PAM_OK;
+}
+
+int pam_destroy(pam_handle* h) {
+    if (!h) return PAM_OK;
+    cudaSetDevice(h->device);
+    h->cam.release();
+    h->ws_state.release(); h->ws_dets.release(); h->ws_counts.release(); h->ws_count.release();
+    h->ws_ids.release(); h->ws_joints.release(); h->ws_nv.release(); h->ws_assoc.release();
+    if (h->ws_stream) cudaStreamDestroy(h->ws_stream);
+    delete h;
+    return PAM_OK;
+}
+
+int pam_set_cameras(pam_handle* h, const float* P, const float* RKinv, const double* pos, const float* F) {
+    if (!h || !P || !RKinv || !pos || !F) return fail(h, PAM_E_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    const int V = h->cfg.num_cameras;
+    const size_t bpos = (size_t)V * 3 * 8, bP = (size_t)V * 12 * 4, bRK = (size_t)V * 9 * 4, bF = (size_t)V * V * 9 * 4;
+    CK(h->cam.reserve(bpos + bP + bRK + bF));
+    char* base = (char*)h->cam.p;
+    CK(cudaMemcpy(base, pos, bpos, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(base + bpos, P, bP, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(base + bpos + bP, RKinv, bRK, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(base + bpos + bP + bRK, F, bF, cudaMemcpyHostToDevice));
+    h->cc.pos = (const double*)base;
+    h->cc.P = (const float*)(base + bpos);
+    h->cc.RKinv = (const float*)(base + bpos + bP);
+    h->cc.F = (const float*)(base + bpos + bP + bRK);
+    h->have_cameras = true;
+    return PAM_OK;
+}
+
+int pam_get_state_layout(const pam_handle* h, pam_state_layout* out) {
+    if (!h || !out) return PAM_E_INVALID;
+    fill_layout(h->dc, *out);
+    return PAM_OK;
+}
+
+int pam_track_reset(pam_handle* h, void* d_state, int32_t S, void* stream) {
+    if (!h || !d_state || S < 0) return fail(h, PAM_E_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(d_state, 0, (size_t)h->dc.seq_bytes * S, (cudaStream_t)stream));
+    return PAM_OK;
+}
+
+int pam_track_sequences(pam_handle* h, void* d_state, int32_t S, int32_t T, int32_t frame0, const float* d_dets,
+                        const int32_t* d_counts, int32_t* d_out_count, int32_t* d_out_ids, float* d_out_joints,
+                        uint8_t* d_out_nviews, int32_t* d_out_assoc, void* stream) {
+    if (!h || !d_state || !d_dets || !d_counts || S < 0 || T < 0) return fail(h, PAM_E_INVALID, "bad argument");
+    if (!h->have_cameras) return fail(h, PAM_E_NOCAMERAS, "pam_set_cameras has not been called");
+    if (S == 0 || T == 0) return PAM_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t smem = (size_t)arena_doubles(h->dc) * sizeof(double);
+    if (smem > 48 * 1024 - sizeof(SeqShared))
+        CK(cudaFuncSetAttribute(k_track_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TrackIO io{d_dets, d_counts, d_out_count, d_out_ids, d_out_joints, d_out_nviews, d_out_assoc};
+    k_track_sequences<<<S, h->track_threads, smem, (cudaStream_t)stream>>>(h->dc, h->cc, (char*)d_state, T, frame0, io);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return PAM_OK;
+}
+
+int pam_track_status(pam_handle* h, const void* d_state, int32_t S, int32_t* h_status, void* stream) {
+    if (!h || !d_state || S < 0) return fail(h, PAM_E_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    std::vector<int32_t> tmp((size_t)S);
+    const char* base = (const char*)d_state + h->dc.off_hdr + offsetof(SeqHeader, status);
+    CK(cudaMemcpy2DAsync(tmp.data(), 4, base, (size_t)h->dc.seq_bytes, 4, (size_t)S, cudaMemcpyDeviceToHost,
+                         (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    int bad = 0, first = -1, code = 0;
+    for (int s = 0; s < S; ++s) {
+        if (h_status) h_status[s] = tmp[s];
+        if (tmp[s] != 0) { if (!bad) { first = s; code = tmp[s]; } ++bad; }
+    }
+    if (bad) {
+        static const char* names[] = {"ok", "track slots exhausted (raise max_tracks)", "hypothesis table exhausted",
+                                      "more detections than max_detections", "pose history ring exhausted"};
+        char msg[256];
+        snprintf(msg, sizeof msg, "%d sequence(s) hit a capacity limit; first: sequence %d: %s", bad, first,
+                 (code >= 0 && code <= 4) ? names[code] : "unknown");
+        return fail(h, PAM_E_CAPACITY, msg);
+    }
+    return PAM_OK;
+}
+
+int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0, int32_t fresh, const float* h_dets,
+                             const int32_t* h_counts, int32_t* h_out_count, int32_t* h_out_ids, float* h_out_joints,
+                             uint8_t* h_out_nviews, int32_t* h_out_assoc) {
+    if (!h || !h_dets || !h_counts || !h_out_count || S <= 0 || T <= 0) return fail(h, PAM_E_INVALID, "bad argument");
+    if (!h->have_cameras) return fail(h, PAM_E_NOCAMERAS, "pam_set_cameras has not been called");
+    CK(cudaSetDevice(h->device));
+    if (!h->ws_stream) CK(cudaStreamCreateWithFlags(&h->ws_stream, cudaStreamNonBlocking));
+    cudaStream_t st = h->ws_stream;
+    const DevCfg& c = h->dc;
+    const size_t ST = (size_t)S * T;
+    const size_t b_dets = ST * c.V * c.D * c.J * 3 * 4, b_counts = ST * c.V * 4, b_count = ST * 4;
+    const size_t b_ids = ST * c.max_trk * 4, b_joints = ST * c.max_trk * c.J * 3 * 4, b_nv = ST * c.max_trk * c.J;
+    const size_t b_assoc = ST * c.V * c.D * 4;
+    if (fresh || S != h->ws_S) {
+        CK(h->ws_state.reserve((size_t)c.seq_bytes * S));
+        CK(cudaMemsetAsync(h->ws_state.p, 0, (size_t)c.seq_bytes * S, st));
+        h->ws_S = S;
+    }
+    CK(h->ws_dets.reserve(b_dets));
+    CK(h->ws_counts.reserve(b_counts));
+    CK(h->ws_count.reserve(b_count));
+    if (h_out_ids) CK(h->ws_ids.reserve(b_ids));
+    if (h_out_joints) CK(h->ws_joints.reserve(b_joints));
+    if (h_out_nviews) CK(h->ws_nv.reserve(b_nv));
+    if (h_out_assoc) CK(h->ws_assoc.reserve(b_assoc));
+    CK(cudaMemcpyAsync(h->ws_dets.p, h_dets, b_dets, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->ws_counts.p, h_counts, b_counts, cudaMemcpyHostToDevice, st));
+    int rc = pam_track_sequences(h, h->ws_state.p, S, T, frame0, (const float*)h->ws_dets.p, (const int32_t*)h->ws_counts.p,
+                                 (int32_t*)h->ws_count.p, h_out_ids ? (int32_t*)h->ws_ids.p : nullptr,
+                                 h_out_joints ? (float*)h->ws_joints.p : nullptr,
+                                 h_out_nviews ? (uint8_t*)h->ws_nv.p : nullptr,
+                                 h_out_assoc ? (int32_t*)h->ws_assoc.p : nullptr, st);
+    if (rc != PAM_OK) return rc;
+    CK(cudaMemcpyAsync(h_out_count, h->ws_count.p, b_count, cudaMemcpyDeviceToHost, st));
+    if (h_out_ids) CK(cudaMemcpyAsync(h_out_ids, h->ws_ids.p, b_ids, cudaMemcpyDeviceToHost, st));
+    if (h_out_joints) CK(cudaMemcpyAsync(h_out_joints, h->ws_joints.p, b_joints, cudaMemcpyDeviceToHost, st));
+    if (h_out_nviews) CK(cudaMemcpyAsync(h_out_nviews, h->ws_nv.p, b_nv, cudaMemcpyDeviceToHost, st));
+    if (h_out_assoc) CK(cudaMemcpyAsync(h_out_assoc, h->ws_assoc.p, b_assoc, cudaMemcpyDeviceToHost, st));
+    return pam_track_status(h, h->ws_state.p, S, nullptr, st);
+}
+
+int pam_track_state_to_host(pam_handle* h, int32_t S, void* h_state) {
+    if (!h || !h_state || S <= 0 || S > h->ws_S) return fail(h, PAM_E_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h_state, h->ws_state.p, (size_t)h->dc.seq_bytes * S, cudaMemcpyDeviceToHost, h->ws_stream));
+    CK(cudaStreamSynchronize(h->ws_stream));
+    return PAM_OK;
+}
+
+int64_t pam_launch_count(const pam_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"
+
+#include "pam_ops_capi.inc"

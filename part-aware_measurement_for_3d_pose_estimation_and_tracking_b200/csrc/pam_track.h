@@ -1,0 +1,714 @@
+// pam_track.h -- one frame of the part-aware tracker for ONE sequence, written block-cooperatively.
+//
+// frame_step<Ctx>() is executed by all threads of one CTA (Ctx = DeviceCtx) which owns one
+// sequence; phases are separated by ctx.sync().  Work inside a phase is a grid-stride loop over
+// independent items (camera x track x detection, track x joint, hypothesis x detection ...), the
+// few inherently serial steps (list bookkeeping, assignment problems) run on one thread per
+// problem.  With Ctx = HostCtx (one "thread", sync = no-op) the same source runs on the CPU under
+// tests/hostemu/ for debugging only.
+//
+// Reference semantics (paths under /root/reference/src):
+//   phase 0-4  tracking/IterativeTracker.py:124-167   ageing, reprojection affinity, LSAP, add_pose
+//   phase 5    tracking/IterativeTracker.py:253-274, 305-395   per-track update
+//   phase 6    tracking/IterativeTracker.py:52-113 + tracking/hypothesis.py:11-77   new-track init
+//   phase 7    tracking/IterativeTracker.py:178 + ivclabpose.py:265-287   reap + output contract
+#pragma once
+#include "pam_core.h"
+
+namespace pam {
+
+enum { ST_TENTATIVE = 1, ST_CONFIRMED = 2, ST_DELETED = 3 };
+enum {
+    SEQ_OK = 0,
+    SEQ_ERR_TRACK_OVERFLOW = 1,   // more live tracks than cfg.max_trk
+    SEQ_ERR_HYP_OVERFLOW = 2,     // more hypotheses than PAM_MAX_HYP
+    SEQ_ERR_DET_OVERFLOW = 3,     // counts[c] > cfg.D
+    SEQ_ERR_HIST_OVERFLOW = 4,    // history ring full (max_age too large for PAM_HIST)
+};
+
+// Launch-constant parameters (kernel argument, < 1 KB).
+struct DevCfg {
+    int V, J, D, max_trk;
+    int n_init, max_age, min_valid, stale_window;
+    uint32_t arm_mask;
+    int rad[2];                              // [0] sigma, [1] arm_sigma
+    double gw[2][PAM_MAX_RADIUS + 1];
+    double w_age[PAM_MAX_AGEW];              // exp(-lambda_t * T), T = 0..stale_window
+    double conf_thr, epi_thr, joint_thr, alpha2d, lambda_a, veto_believe, fail_limit;
+    float init_thr_f32;
+    // per-sequence global state strides (bytes) -- see state_layout()
+    int64_t off_hdr, off_meta, off_view, off_hist, off_vel, off_nv, seq_bytes;
+};
+
+struct SeqHeader {
+    int ntracks, next_id, status, frames_done;
+    uint32_t used_mask;
+    int order[PAM_MAX_TRK];
+};
+
+struct TrkMeta {
+    int track_id, hits, age, tsu, state, already, nviews, hist_start, hist_len;
+    int view_cid[PAM_MAX_V];
+    int view_time[PAM_MAX_V];
+    int hist_time[PAM_HIST];
+};
+
+inline void state_layout(DevCfg& c) {
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) { int64_t at = o; o += (bytes + 15) / 16 * 16; return at; };
+    c.off_hdr = take(sizeof(SeqHeader));
+    c.off_meta = take((int64_t)sizeof(TrkMeta) * c.max_trk);
+    c.off_hist = take((int64_t)8 * c.max_trk * PAM_HIST * c.J * 3);
+    c.off_view = take((int64_t)4 * c.max_trk * c.V * c.J * 3);
+    c.off_vel = take((int64_t)4 * c.max_trk * c.J * 3);
+    c.off_nv = take((int64_t)c.max_trk * c.J);
+    c.seq_bytes = (o + 127) / 128 * 128;
+}
+
+// Global-memory views of one sequence's state.
+struct SeqGlobal {
+    SeqHeader* hdr;
+    TrkMeta* meta;
+    double* hist;     // [max_trk][PAM_HIST][J][3]
+    float* view;      // [max_trk][V][J][3]  (v, u, conf)
+    float* vel;       // [max_trk][J][3]
+    unsigned char* nv;  // [max_trk][J]
+    PAM_HD void bind(const DevCfg& c, char* base) {
+        hdr = (SeqHeader*)(base + c.off_hdr);
+        meta = (TrkMeta*)(base + c.off_meta);
+        hist = (double*)(base + c.off_hist);
+        view = (float*)(base + c.off_view);
+        vel = (float*)(base + c.off_vel);
+        nv = (unsigned char*)(base + c.off_nv);
+    }
+};
+
+// Per-frame outputs of one sequence (any pointer may be null).
+struct FrameOut {
+    int* count;            // [1]
+    int* ids;              // [max_trk]
+    float* joints;         // [max_trk][J][3]
+    unsigned char* nviews; // [max_trk][J]
+    int* assoc;            // [V][D]  track id matched to each detection, -1 = unmatched
+};
+
+// Block-shared working set.  Fixed-size part; the J-dependent arrays live in `arena`.
+struct SeqShared {
+    SeqHeader hdr;
+    TrkMeta trk[PAM_MAX_TRK];
+    double P[PAM_MAX_V][12];
+    double RK[PAM_MAX_V][9];
+    double pos[PAM_MAX_V][3];
+    double F[PAM_MAX_V][PAM_MAX_V][9];
+    // frame scratch
+    int n;                                   // tracks alive at frame start
+    int m[PAM_MAX_V];                        // detections per camera
+    int dt[PAM_MAX_TRK];
+    int last[PAM_MAX_TRK];                   // ring index of the last pose
+    int newpos[PAM_MAX_TRK];                 // ring index the new pose goes to
+    signed char t2d[PAM_MAX_V][PAM_MAX_TRK];
+    signed char d2t[PAM_MAX_V][PAM_MAX_D];
+    signed char vk[PAM_MAX_V][PAM_MAX_TRK];  // view slot written by add_pose
+    signed char gv_idx[PAM_MAX_TRK][PAM_MAX_V];
+    int gv_n[PAM_MAX_TRK];
+    int do_update[PAM_MAX_TRK];
+    int ok[PAM_MAX_TRK];
+    unsigned char nvj[PAM_MAX_TRK][PAM_MAX_J];
+    // init
+    double believe[PAM_MAX_V][PAM_MAX_D];
+    unsigned char um_flag[PAM_MAX_V][PAM_MAX_D];
+    signed char um[PAM_MAX_V][PAM_MAX_D];
+    int um_n[PAM_MAX_V];
+    int do_init;
+    int hyp_n;
+    int hyp_nviews[PAM_MAX_HYP];
+    signed char hyp_cam[PAM_MAX_HYP][PAM_MAX_V];
+    signed char hyp_det[PAM_MAX_HYP][PAM_MAX_V];
+    unsigned char hyp_fail[PAM_MAX_HYP];
+    signed char hyp_slot[PAM_MAX_HYP];
+    unsigned char hyp_veto[PAM_MAX_HYP][PAM_MAX_D];
+    unsigned char hyp_nvj[PAM_MAX_HYP][PAM_MAX_J];
+    double hyp_cost[PAM_MAX_HYP][PAM_MAX_D];
+    // output
+    int out_n;
+    signed char out_slot[PAM_MAX_TRK];
+    // arena pointers (set by carve())
+    double* aff;      // [V][max_trk][D]
+    double* reproj;   // [V][max_trk][J][2]   (v, u)
+    double* raw;      // [max_trk][J][3]
+    double* hyp_pose; // [PAM_MAX_HYP][J][3]  (aliases reproj: phases do not overlap)
+};
+
+PAM_HD int64_t arena_doubles(const DevCfg& c) {
+    int64_t a = (int64_t)c.V * c.max_trk * c.D;
+    int64_t r = (int64_t)c.V * c.max_trk * c.J * 2;
+    int64_t h = (int64_t)PAM_MAX_HYP * c.J * 3;
+    int64_t w = (int64_t)c.max_trk * c.J * 3;
+    return a + (r > h ? r : h) + w;
+}
+PAM_HD void carve(const DevCfg& c, SeqShared& sh, double* arena) {
+    int64_t r = (int64_t)c.V * c.max_trk * c.J * 2;
+    int64_t h = (int64_t)PAM_MAX_HYP * c.J * 3;
+    sh.aff = arena;
+    sh.reproj = sh.aff + (int64_t)c.V * c.max_trk * c.D;
+    sh.hyp_pose = sh.reproj;
+    sh.raw = sh.reproj + (r > h ? r : h);
+}
+
+struct HostCtx {
+    inline int tid() const { return 0; }
+    inline int nthreads() const { return 1; }
+    inline void sync() const {}
+};
+
+#define PAM_FOR(i, N) for (int i = ctx.tid(), _n_##i = (N), _s_##i = ctx.nthreads(); i < _n_##i; i += _s_##i)
+
+// camera constants: f32 in global memory (the reference's dtypes), widened once into shared.
+struct CamConst {
+    const float* P;      // [V][12]
+    const float* RKinv;  // [V][9]
+    const double* pos;   // [V][3]
+    const float* F;      // [V][V][9]
+};
+
+template <class Ctx>
+PAM_HD void load_cameras(Ctx& ctx, const DevCfg& c, SeqShared& sh, const CamConst& cc) {
+    PAM_FOR(i, c.V * 12) sh.P[i / 12][i % 12] = (double)cc.P[i];
+    PAM_FOR(i, c.V * 9) sh.RK[i / 9][i % 9] = (double)cc.RKinv[i];
+    PAM_FOR(i, c.V * 3) sh.pos[i / 3][i % 3] = cc.pos[i];
+    PAM_FOR(i, c.V * c.V * 9) sh.F[i / (9 * c.V)][(i / 9) % c.V][i % 9] = (double)cc.F[i];
+}
+
+template <class Ctx>
+PAM_HD void load_state(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal& g) {
+    const int* src = (const int*)g.hdr;
+    int* dst = (int*)&sh.hdr;
+    PAM_FOR(i, (int)(sizeof(SeqHeader) / 4)) dst[i] = src[i];
+    const int* srcm = (const int*)g.meta;
+    int* dstm = (int*)sh.trk;
+    PAM_FOR(i, (int)(sizeof(TrkMeta) / 4) * c.max_trk) dstm[i] = srcm[i];
+}
+
+template <class Ctx>
+PAM_HD void store_state(Ctx& ctx, const DevCfg& c, const SeqShared& sh, const SeqGlobal& g) {
+    int* dst = (int*)g.hdr;
+    const int* src = (const int*)&sh.hdr;
+    PAM_FOR(i, (int)(sizeof(SeqHeader) / 4)) dst[i] = src[i];
+    int* dstm = (int*)g.meta;
+    const int* srcm = (const int*)sh.trk;
+    PAM_FOR(i, (int)(sizeof(TrkMeta) / 4) * c.max_trk) dstm[i] = srcm[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// per-joint pieces of the update / init paths
+// ------------------------------------------------------------------------------------------
+
+// Part-aware view filter + DLT for one joint of one track (update mode).
+//   views 0..Vt-1 in the track's dict order; cid/T per view; (u, v) per view; next = predicted joint.
+// Returns the number of surviving views; X = triangulated joint (or `next` when < 2 views).
+PAM_HD int joint_update(const DevCfg& c, const SeqShared& sh, int Vt, const int* cid, const int* T,
+                        const double* u, const double* v, const double* next, double* X) {
+    uint32_t conflict[PAM_MAX_V];
+    for (int a = 0; a < Vt; ++a) conflict[a] = 0u;
+    bool any = false;
+    for (int a = 0; a < Vt; ++a)
+        for (int b = a + 1; b < Vt; ++b) {
+            double dab = epi_dist_f64(sh.F[cid[a]][cid[b]], u[a], v[a], u[b], v[b]);
+            double dba = epi_dist_f64(sh.F[cid[b]][cid[a]], u[b], v[b], u[a], v[a]);
+            double D = (dab + dba) / 2.0;
+            double A = 1.0 - D / c.joint_thr;
+            if (A < 0.0) { conflict[a] |= (1u << b); any = true; }
+        }
+    uint32_t alive = (Vt >= 32) ? 0xffffffffu : ((1u << Vt) - 1u);
+    if (any) {
+        double rd[PAM_MAX_V];
+        for (int a = 0; a < Vt; ++a) rd[a] = 0.0;
+        for (int a = 0; a < Vt; ++a)
+            for (int b = a + 1; b < Vt; ++b) {
+                if (!((conflict[a] >> b) & 1u)) continue;
+                if (!((alive >> a) & 1u) || !((alive >> b) & 1u)) continue;
+                if (rd[a] == 0.0) rd[a] = ray_point_distance(sh.RK[cid[a]], sh.pos[cid[a]], u[a], v[a], next);
+                if (rd[b] == 0.0) rd[b] = ray_point_distance(sh.RK[cid[b]], sh.pos[cid[b]], u[b], v[b], next);
+                if (rd[a] > rd[b]) alive &= ~(1u << a); else alive &= ~(1u << b);
+            }
+    }
+    int nv = 0;
+    for (int a = 0; a < Vt; ++a) nv += (alive >> a) & 1u;
+    if (nv < 2) {
+        X[0] = next[0]; X[1] = next[1]; X[2] = next[2];
+        return nv;
+    }
+    DltAccum acc;
+    acc.reset();
+    for (int a = 0; a < Vt; ++a)
+        if ((alive >> a) & 1u) acc.add_view(sh.P[cid[a]], u[a], v[a], c.w_age[T[a]]);
+    acc.solve(X);
+    return nv;
+}
+
+// Same for a hypothesis (init mode, float32 affinities, row-sum rule).  Returns surviving views.
+PAM_HD int joint_init(const DevCfg& c, const SeqShared& sh, int Vt, const signed char* cid,
+                      const double* u, const double* v, double* X) {
+    float A[PAM_MAX_V][PAM_MAX_V];
+    bool any = false;
+    for (int a = 0; a < Vt; ++a) {
+        A[a][a] = 1.0f - 0.0f / c.init_thr_f32;
+        for (int b = a + 1; b < Vt; ++b) {
+            double d1, d2;
+            epi_pair_cv(sh.F[cid[a]][cid[b]], u[a], v[a], u[b], v[b], d1, d2);
+            float Df = (float)((d1 + d2) / 2.0);
+            float Af = 1.0f - Df / c.init_thr_f32;
+            A[a][b] = Af; A[b][a] = Af;
+            if (Af < 0.0f) any = true;
+        }
+    }
+    uint32_t alive = (1u << Vt) - 1u;
+    if (any) {
+        for (int a = 0; a < Vt; ++a)
+            for (int b = a + 1; b < Vt; ++b) {
+                if (!(A[a][b] < 0.0f)) continue;
+                if (!((alive >> a) & 1u) || !((alive >> b) & 1u)) continue;
+                float s1 = np_sum(A[a], Vt), s2 = np_sum(A[b], Vt);
+                if (s1 > s2) alive &= ~(1u << b); else alive &= ~(1u << a);
+            }
+    }
+    int nv = 0;
+    for (int a = 0; a < Vt; ++a) nv += (alive >> a) & 1u;
+    if (nv < 2) return nv;
+    DltAccum acc;
+    acc.reset();
+    for (int a = 0; a < Vt; ++a)
+        if ((alive >> a) & 1u) acc.add_view(sh.P[cid[a]], u[a], v[a], c.w_age[0]);
+    acc.solve(X);
+    return nv;
+}
+
+// Hypothesis.calculate_cost for hypothesis h against detection (cam c2, pose o) of this frame.
+PAM_HD double hyp_cost(const DevCfg& c, const SeqShared& sh, const float* dets, int h, int c2, int d2,
+                       bool& veto) {
+    const int J = c.J;
+    const float* o = dets + ((int64_t)(c2 * c.D + d2) * J) * 3;
+    double total = 0.0;
+    veto = false;
+    const int nvw = sh.hyp_nviews[h];
+    for (int k = 0; k < nvw; ++k) {
+        const int c1 = sh.hyp_cam[h][k];
+        const float* p = dets + ((int64_t)(c1 * c.D + sh.hyp_det[h][k]) * J) * 3;
+        NpSumStream<double> acc;
+        acc.begin(J);
+        for (int j = 0; j < J; ++j) {
+            double d1, d2v;
+            epi_pair_cv(sh.F[c1][c2], (double)p[j * 3 + 1], (double)p[j * 3 + 0], (double)o[j * 3 + 1],
+                        (double)o[j * 3 + 0], d1, d2v);
+            acc.push((d1 * (double)p[j * 3 + 2] + d2v * (double)o[j * 3 + 2]) / 2.0);
+        }
+        double pc = acc.total() / (double)J / c.epi_thr;
+        total += pc;
+        if (pc > 1.0 && sh.believe[c2][d2] > c.veto_believe) veto = true;
+    }
+    return total / (double)nvw;
+}
+
+// ------------------------------------------------------------------------------------------
+// the frame
+// ------------------------------------------------------------------------------------------
+template <class Ctx>
+PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal& g, int frame,
+                       const float* dets /* [V][D][J][3] */, const int* counts /* [V] */, const FrameOut& out) {
+    const int V = c.V, J = c.J, D = c.D, MT = c.max_trk;
+    const int J3 = J * 3;
+    if (sh.hdr.status != SEQ_OK) {   // uniform: status only changes between syncs
+        if (ctx.tid() == 0 && out.count) *out.count = 0;
+        return;
+    }
+
+    // ---- phase 0: ageing + snapshot (IterativeTracker.py:126-129) ------------------------------
+    const int n = sh.hdr.ntracks;
+    PAM_FOR(i, n) {
+        TrkMeta& t = sh.trk[sh.hdr.order[i]];
+        t.already = 0; t.age += 1; t.tsu += 1;
+        int last = (t.hist_start + t.hist_len - 1) % PAM_HIST;
+        sh.last[i] = last;
+        sh.dt[i] = frame - t.hist_time[last];
+    }
+    PAM_FOR(cc, V) {
+        int mm = counts[cc];
+        if (mm > D || mm < 0) { sh.hdr.status = SEQ_ERR_DET_OVERFLOW; mm = 0; }
+        sh.m[cc] = mm;
+    }
+    PAM_FOR(i, V * MT) sh.t2d[i / MT][i % MT] = -1;
+    PAM_FOR(i, V * D) sh.d2t[i / D][i % D] = -1;
+    ctx.sync();
+
+    if (n > 0) {
+        // ---- phase 1: reprojection of every track joint into every camera (ivclabpose.py:91-98)
+        PAM_FOR(it, V * n * J) {
+            const int cam = it / (n * J), i = (it / J) % n, j = it % J;
+            if (sh.m[cam] == 0) continue;
+            const double* X = g.hist + ((int64_t)(sh.hdr.order[i] * PAM_HIST + sh.last[i]) * J + j) * 3;
+            const double* P = sh.P[cam];
+            double a = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[3];
+            double b = P[4] * X[0] + P[5] * X[1] + P[6] * X[2] + P[7];
+            double w = P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11];
+            double* r = sh.reproj + ((int64_t)(cam * MT + i) * J + j) * 2;
+            r[0] = b / w;   // v
+            r[1] = a / w;   // u
+        }
+        ctx.sync();
+
+        // ---- phase 2: track x detection affinity (IterativeTracker.py:139-149) ------------------
+        PAM_FOR(it, V * n * D) {
+            const int cam = it / (n * D), i = (it / D) % n, d = it % D;
+            if (d >= sh.m[cam]) continue;
+            const double* r = sh.reproj + (int64_t)(cam * MT + i) * J * 2;
+            const float* q = dets + (int64_t)(cam * D + d) * J3;
+            const double denom = c.alpha2d * (double)sh.dt[i];
+            double sum = 0.0;
+            int cnt = 0;
+            for (int j = 0; j < J; ++j) {
+                double dv = r[j * 2 + 0] - (double)q[j * 3 + 0];
+                double du = r[j * 2 + 1] - (double)q[j * 3 + 1];
+                double cj = 1.0 - sqrt(dv * dv + du * du) / denom;
+                if (cj > 0.0) { sum += cj; ++cnt; }
+            }
+            double a = (cnt > c.min_valid) ? sum / (double)cnt : 0.0;
+            a = a / exp(c.lambda_a * (double)sh.dt[i]);
+            if (a != a) a = 0.0;
+            sh.aff[(int64_t)(cam * MT + i) * D + d] = a;
+        }
+        ctx.sync();
+
+        // ---- phase 3: one assignment problem per camera (IterativeTracker.py:150-160) -----------
+        PAM_FOR(cam, V) {
+            const int mm = sh.m[cam];
+            if (mm == 0) continue;
+            const double* A = sh.aff + (int64_t)cam * MT * D;
+            int col4row[PAM_MAX_TRK];
+            lsap_solve<PAM_MAX_TRK>(n, mm, [&](int i, int d) { return -A[i * D + d]; }, col4row);
+            for (int i = 0; i < n; ++i) {
+                int d = col4row[i];
+                if (d >= 0 && A[i * D + d] > 0.0) { sh.t2d[cam][i] = (signed char)d; sh.d2t[cam][d] = (signed char)i; }
+            }
+        }
+        ctx.sync();
+
+        // ---- phase 4: add_pose in camera order (IterativeTracker.py:289-298) ---------------------
+        PAM_FOR(i, n) {
+            TrkMeta& t = sh.trk[sh.hdr.order[i]];
+            for (int cam = 0; cam < V; ++cam) {
+                if (sh.t2d[cam][i] < 0) continue;
+                int k = 0;
+                while (k < t.nviews && t.view_cid[k] != cam) ++k;
+                if (k == t.nviews) { t.nviews = k + 1; t.view_cid[k] = cam; }
+                t.view_time[k] = frame;
+                t.already = 1;
+                sh.vk[cam][i] = (signed char)k;
+            }
+        }
+        ctx.sync();
+        PAM_FOR(it, V * n * J3) {
+            const int cam = it / (n * J3), i = (it / J3) % n, e = it % J3;
+            const int d = sh.t2d[cam][i];
+            if (d < 0) continue;
+            g.view[((int64_t)(sh.hdr.order[i] * V + sh.vk[cam][i])) * J3 + e] = dets[(int64_t)(cam * D + d) * J3 + e];
+        }
+    }
+    if (out.assoc) {
+        PAM_FOR(it, V * D) {
+            const int cam = it / D, d = it % D;
+            int i = (d < sh.m[cam]) ? sh.d2t[cam][d] : -1;
+            out.assoc[it] = (i >= 0) ? sh.trk[sh.hdr.order[i]].track_id : -1;
+        }
+    }
+
+    // ---- phase 5a: gather usable views per track (IterativeTracker.py:310-325) ------------------
+    PAM_FOR(i, n) {
+        const TrkMeta& t = sh.trk[sh.hdr.order[i]];
+        int cnt = 0;
+        if (t.already)
+            for (int k = 0; k < t.nviews; ++k)
+                if (frame - t.view_time[k] <= c.stale_window) sh.gv_idx[i][cnt++] = (signed char)k;
+        sh.gv_n[i] = cnt;
+        sh.do_update[i] = (t.already && cnt >= 2) ? 1 : 0;
+        sh.ok[i] = 0;
+    }
+    ctx.sync();
+
+    // ---- phase 5b: per (track, joint): part-aware view filter + DLT (IterativeTracker.py:337-369)
+    PAM_FOR(it, n * J) {
+        const int i = it / J, j = it % J;
+        if (!sh.do_update[i]) continue;
+        const int s = sh.hdr.order[i];
+        const TrkMeta& t = sh.trk[s];
+        const double* Xl = g.hist + ((int64_t)(s * PAM_HIST + sh.last[i]) * J + j) * 3;
+        const float* vel = g.vel + (int64_t)(s * J + j) * 3;
+        const float fdt = (float)sh.dt[i];
+        double next[3];
+        for (int k = 0; k < 3; ++k) next[k] = Xl[k] + (double)(vel[k] * fdt);
+        int cid[PAM_MAX_V], T[PAM_MAX_V];
+        double u[PAM_MAX_V], v[PAM_MAX_V];
+        const int Vt = sh.gv_n[i];
+        for (int a = 0; a < Vt; ++a) {
+            const int k = sh.gv_idx[i][a];
+            cid[a] = t.view_cid[k];
+            T[a] = frame - t.view_time[k];
+            const float* q = g.view + ((int64_t)(s * V + k) * J + j) * 3;
+            v[a] = (double)q[0];
+            u[a] = (double)q[1];
+        }
+        double X[3];
+        int nv = joint_update(c, sh, Vt, cid, T, u, v, next, X);
+        sh.nvj[i][j] = (unsigned char)nv;
+        double* r = sh.raw + (int64_t)(i * J + j) * 3;
+        r[0] = X[0]; r[1] = X[1]; r[2] = X[2];
+    }
+    ctx.sync();
+
+    // ---- phase 5c: success test, ring slot for the new pose ------------------------------------
+    PAM_FOR(i, n) {
+        if (!sh.do_update[i]) continue;
+        TrkMeta& t = sh.trk[sh.hdr.order[i]];
+        int fail = 0;
+        for (int j = 0; j < J; ++j) fail += (sh.nvj[i][j] < 2) ? 1 : 0;
+        if ((double)fail > c.fail_limit) continue;
+        if (t.hist_len >= PAM_HIST) { sh.hdr.status = SEQ_ERR_HIST_OVERFLOW; continue; }
+        sh.ok[i] = 1;
+        const int pos = (t.hist_start + t.hist_len) % PAM_HIST;
+        sh.newpos[i] = pos;
+        t.hist_time[pos] = frame;
+    }
+    ctx.sync();
+
+    // ---- phase 5d: temporal Gaussian, last sample (IterativeTracker.py:371-383) -----------------
+    PAM_FOR(it, n * J) {
+        const int i = it / J, j = it % J;
+        if (!sh.ok[i]) continue;
+        const int s = sh.hdr.order[i];
+        const TrkMeta& t = sh.trk[s];
+        const int which = (c.arm_mask >> j) & 1u;
+        const int rad = c.rad[which];
+        const double* w = c.gw[which];
+        const int L = t.hist_len, N = L + 1;       // series = history + current raw pose
+        const double* raw = sh.raw + (int64_t)(i * J + j) * 3;
+        double* dst = g.hist + ((int64_t)(s * PAM_HIST + sh.newpos[i]) * J + j) * 3;
+        double o0 = raw[0] * w[0], o1 = raw[1] * w[0], o2 = raw[2] * w[0];
+        for (int k = rad; k >= 1; --k) {
+            const int il = reflect_index(L - k, N), ir = reflect_index(L + k, N);
+            const double* xl = (il == L) ? raw : g.hist + ((int64_t)(s * PAM_HIST + (t.hist_start + il) % PAM_HIST) * J + j) * 3;
+            const double* xr = (ir == L) ? raw : g.hist + ((int64_t)(s * PAM_HIST + (t.hist_start + ir) % PAM_HIST) * J + j) * 3;
+            o0 += (xl[0] + xr[0]) * w[k];
+            o1 += (xl[1] + xr[1]) * w[k];
+            o2 += (xl[2] + xr[2]) * w[k];
+        }
+        dst[0] = o0; dst[1] = o1; dst[2] = o2;
+        g.nv[s * J + j] = sh.nvj[i][j];
+    }
+    ctx.sync();
+
+    // ---- phase 5e: history trim + life-cycle (IterativeTracker.py:253-274, 329-333) -------------
+    PAM_FOR(i, n) {
+        TrkMeta& t = sh.trk[sh.hdr.order[i]];
+        if (sh.ok[i]) {
+            t.hist_len += 1;
+            if (frame - t.hist_time[t.hist_start] > c.max_age) {
+                t.hist_start = (t.hist_start + 1) % PAM_HIST;
+                t.hist_len -= 1;
+            }
+            t.hits += 1;
+            t.tsu = 0;
+            if (t.state == ST_TENTATIVE && t.hits >= c.n_init) t.state = ST_CONFIRMED;
+        } else {
+            if (t.state == ST_TENTATIVE && !t.already) t.state = ST_DELETED;
+            else if (t.tsu >= c.max_age) t.state = ST_DELETED;
+        }
+    }
+    ctx.sync();
+
+    // ---- phase 5f: velocity = float32 mean of the last <= 5 differences (IterativeTracker.py:385-395)
+    PAM_FOR(it, n * J) {
+        const int i = it / J, j = it % J;
+        if (!sh.ok[i]) continue;
+        const int s = sh.hdr.order[i];
+        const TrkMeta& t = sh.trk[s];
+        if (t.hist_len < 2) continue;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        int cnt = 0;
+        for (int idx = t.hist_len - 1; idx >= 1 && cnt < 5; --idx, ++cnt) {
+            const double* hi = g.hist + ((int64_t)(s * PAM_HIST + (t.hist_start + idx) % PAM_HIST) * J + j) * 3;
+            const double* lo = g.hist + ((int64_t)(s * PAM_HIST + (t.hist_start + idx - 1) % PAM_HIST) * J + j) * 3;
+            a0 += (float)hi[0] - (float)lo[0];
+            a1 += (float)hi[1] - (float)lo[1];
+            a2 += (float)hi[2] - (float)lo[2];
+        }
+        float* vel = g.vel + (int64_t)(s * J + j) * 3;
+        const float fc = (float)cnt;
+        vel[0] = a0 / fc; vel[1] = a1 / fc; vel[2] = a2 / fc;
+    }
+
+    // ---- phase 6: new-track initialisation (IterativeTracker.py:52-113) -------------------------
+    // 6a: mean confidence of every detection; unmatched + confident ones take part
+    PAM_FOR(it, V * D) {
+        const int cam = it / D, d = it % D;
+        sh.um_flag[cam][d] = 0;
+        if (d >= sh.m[cam]) continue;
+        const float* q = dets + (int64_t)(cam * D + d) * J3;
+        double kept[PAM_MAX_J];
+        int nk = 0;
+        for (int j = 0; j < J; ++j)
+            if (q[j * 3 + 2] >= 0.0f) kept[nk++] = (double)q[j * 3 + 2];
+        double b = np_sum(kept, nk) / (double)nk;   // 0/0 -> NaN like np.mean([])
+        sh.believe[cam][d] = b;
+        sh.um_flag[cam][d] = (sh.d2t[cam][d] < 0 && b > c.conf_thr) ? 1 : 0;
+    }
+    ctx.sync();
+    if (ctx.tid() == 0) {
+        int cams_with = 0;
+        for (int cam = 0; cam < V; ++cam) {
+            int k = 0;
+            for (int d = 0; d < sh.m[cam]; ++d)
+                if (sh.um_flag[cam][d]) sh.um[cam][k++] = (signed char)d;
+            sh.um_n[cam] = k;
+            cams_with += (k > 0);
+        }
+        // a hypothesis needs views from two cameras to become a track (hypothesis.size() > 1)
+        sh.do_init = (V >= 2 && cams_with >= 2) ? 1 : 0;
+        sh.hyp_n = 0;
+        if (sh.do_init) {
+            for (int k = 0; k < sh.um_n[0]; ++k) {
+                sh.hyp_nviews[k] = 1; sh.hyp_cam[k][0] = 0; sh.hyp_det[k][0] = sh.um[0][k];
+            }
+            sh.hyp_n = sh.um_n[0];
+        }
+    }
+    ctx.sync();
+    if (sh.do_init) {
+        // 6c: grow hypotheses camera by camera
+        for (int cam = 1; cam < V; ++cam) {
+            const int nh = sh.hyp_n, nd = sh.um_n[cam];
+            if (nd == 0) continue;           // uniform
+            PAM_FOR(it, nh * nd) {
+                const int h = it / nd, p = it % nd;
+                bool veto;
+                sh.hyp_cost[h][p] = hyp_cost(c, sh, dets, h, cam, sh.um[cam][p], veto);
+                sh.hyp_veto[h][p] = veto ? 1 : 0;
+            }
+            ctx.sync();
+            if (ctx.tid() == 0) {
+                int col4row[PAM_MAX_HYP];
+                uint32_t handled = 0u;
+                lsap_solve<PAM_MAX_HYP>(nh, nd, [&](int h, int p) { return sh.hyp_cost[h][p]; }, col4row);
+                int hn = nh;
+                for (int h = 0; h < nh; ++h) {
+                    const int p = col4row[h];
+                    if (p < 0) continue;
+                    handled |= (1u << p);
+                    if (sh.hyp_veto[h][p]) {
+                        if (hn >= PAM_MAX_HYP) { sh.hdr.status = SEQ_ERR_HYP_OVERFLOW; break; }
+                        sh.hyp_nviews[hn] = 1; sh.hyp_cam[hn][0] = (signed char)cam; sh.hyp_det[hn][0] = sh.um[cam][p];
+                        ++hn;
+                    } else {
+                        const int k = sh.hyp_nviews[h]++;
+                        sh.hyp_cam[h][k] = (signed char)cam; sh.hyp_det[h][k] = sh.um[cam][p];
+                    }
+                }
+                for (int p = 0; p < nd; ++p) {
+                    if ((handled >> p) & 1u) continue;
+                    if (hn >= PAM_MAX_HYP) { sh.hdr.status = SEQ_ERR_HYP_OVERFLOW; break; }
+                    sh.hyp_nviews[hn] = 1; sh.hyp_cam[hn][0] = (signed char)cam; sh.hyp_det[hn][0] = sh.um[cam][p];
+                    ++hn;
+                }
+                sh.hyp_n = hn;
+            }
+            ctx.sync();
+        }
+        // 6d: first triangulation of every multi-view hypothesis (hypothesis.py:23-44)
+        const int nh = sh.hyp_n;
+        PAM_FOR(h, nh) sh.hyp_fail[h] = (sh.hyp_nviews[h] < 2) ? 1 : 0;
+        ctx.sync();
+        PAM_FOR(it, nh * J) {
+            const int h = it / J, j = it % J;
+            const int Vt = sh.hyp_nviews[h];
+            if (Vt < 2) continue;
+            double u[PAM_MAX_V], v[PAM_MAX_V];
+            for (int a = 0; a < Vt; ++a) {
+                const float* q = dets + ((int64_t)(sh.hyp_cam[h][a] * D + sh.hyp_det[h][a]) * J + j) * 3;
+                v[a] = (double)q[0];
+                u[a] = (double)q[1];
+            }
+            double X[3] = {0.0, 0.0, 0.0};
+            const int nv = joint_init(c, sh, Vt, sh.hyp_cam[h], u, v, X);
+            sh.hyp_nvj[h][j] = (unsigned char)nv;
+            if (nv < 2) sh.hyp_fail[h] = 1;     // benign race: every writer stores 1
+            double* r = sh.hyp_pose + (int64_t)(h * J + j) * 3;
+            r[0] = X[0]; r[1] = X[1]; r[2] = X[2];
+        }
+        ctx.sync();
+        // 6e: spawn tracks in hypothesis order (IterativeTracker.py:102-113)
+        if (ctx.tid() == 0) {
+            for (int h = 0; h < nh; ++h) {
+                sh.hyp_slot[h] = -1;
+                if (sh.hyp_fail[h] || sh.hdr.status != SEQ_OK) continue;
+                int s = 0;
+                while (s < MT && ((sh.hdr.used_mask >> s) & 1u)) ++s;
+                if (s >= MT || sh.hdr.ntracks >= MT) { sh.hdr.status = SEQ_ERR_TRACK_OVERFLOW; continue; }
+                sh.hdr.used_mask |= (1u << s);
+                sh.hdr.order[sh.hdr.ntracks++] = s;
+                TrkMeta& t = sh.trk[s];
+                t.track_id = sh.hdr.next_id++;
+                t.hits = 1; t.age = 1; t.tsu = 0; t.state = ST_TENTATIVE; t.already = 0;
+                t.nviews = sh.hyp_nviews[h];
+                for (int k = 0; k < t.nviews; ++k) { t.view_cid[k] = sh.hyp_cam[h][k]; t.view_time[k] = frame; }
+                t.hist_start = 0; t.hist_len = 1; t.hist_time[0] = frame;
+                sh.hyp_slot[h] = (signed char)s;
+            }
+        }
+        ctx.sync();
+        PAM_FOR(it, nh * J3) {
+            const int h = it / J3, e = it % J3;
+            const int s = sh.hyp_slot[h];
+            if (s < 0) continue;
+            for (int k = 0; k < sh.hyp_nviews[h]; ++k)
+                g.view[(int64_t)(s * V + k) * J3 + e] = dets[(int64_t)(sh.hyp_cam[h][k] * D + sh.hyp_det[h][k]) * J3 + e];
+            g.hist[(int64_t)(s * PAM_HIST) * J3 + e] = sh.hyp_pose[(int64_t)h * J3 + e];
+            g.vel[(int64_t)s * J3 + e] = 0.0f;
+            if (e < J) g.nv[s * J + e] = sh.hyp_nvj[h][e];
+        }
+    }
+    ctx.sync();
+
+    // ---- phase 7: output contract + reap (ivclabpose.py:265-287, IterativeTracker.py:178) -------
+    if (ctx.tid() == 0) {
+        int k = 0, w = 0;
+        for (int i = 0; i < sh.hdr.ntracks; ++i) {
+            const int s = sh.hdr.order[i];
+            const TrkMeta& t = sh.trk[s];
+            if (t.state == ST_CONFIRMED && t.tsu == 0) {
+                sh.out_slot[k] = (signed char)s;
+                if (out.ids) out.ids[k] = t.track_id;
+                ++k;
+            }
+            if (t.state == ST_DELETED) sh.hdr.used_mask &= ~(1u << s);
+            else sh.hdr.order[w++] = s;
+        }
+        sh.hdr.ntracks = w;
+        sh.out_n = k;
+        sh.hdr.frames_done += 1;
+        if (out.count) *out.count = k;
+    }
+    ctx.sync();
+    if (out.joints) {
+        PAM_FOR(it, sh.out_n * J3) {
+            const int k = it / J3, e = it % J3;
+            const int s = sh.out_slot[k];
+            const TrkMeta& t = sh.trk[s];
+            const int last = (t.hist_start + t.hist_len - 1) % PAM_HIST;
+            out.joints[it] = (float)g.hist[(int64_t)(s * PAM_HIST + last) * J3 + e];
+        }
+    }
+    if (out.nviews) {
+        PAM_FOR(it, sh.out_n * J) out.nviews[it] = g.nv[sh.out_slot[it / J] * J + it % J];
+    }
+    ctx.sync();
+}
+
+}  // namespace pam

@@ -14,7 +14,7 @@ buffers see *identical* numbers.
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
@@ -203,12 +203,15 @@ class Stream:
 
 def make_stream(shape: "Shape | str", seq_id: int = 0, T: Optional[int] = None, *, noise_px: float = 1.0,
                 miss_prob: float = 0.02, outlier_prob: float = 0.01, outlier_px: float = 50.0,
-                rig: Optional[dict] = None, enter_stagger: int = 0, P: Optional[int] = None) -> Stream:
+                rig: Optional[dict] = None, enter_stagger: int = 0, P: Optional[int] = None,
+                absences: Sequence = ()) -> Stream:
     """One seeded sequence of ``T`` frames.
 
     ``enter_stagger`` > 0 makes person ``p`` appear only from frame ``p * enter_stagger`` on,
     which exercises new-track initialisation (src/tracking/IterativeTracker.py:52-113) in the
-    middle of a stream."""
+    middle of a stream.  ``absences`` = ``[(person, t0, t1), ...]`` removes a person from every
+    camera for frames ``t0 <= t < t1`` (track ageing, deletion after ``max_age`` and re-entry under a
+    fresh id, src/tracking/IterativeTracker.py:268-274,108-113)."""
     sh = SHAPES[shape] if isinstance(shape, str) else shape
     T = sh.T if T is None else T
     P = sh.P if P is None else P
@@ -262,6 +265,8 @@ def make_stream(shape: "Shape | str", seq_id: int = 0, T: Optional[int] = None, 
     present = rng.random(size=(T, V, P)) >= miss_prob
     if enter_stagger > 0:
         present &= (np.arange(T)[:, None, None] >= (np.arange(P) * enter_stagger)[None, None, :])
+    for (p, t0, t1) in absences:
+        present[t0:t1, :, p] = False
     order = np.argsort(rng.random(size=(T, V, P)), axis=-1)     # random person order per camera/frame
 
     D = P
@@ -277,7 +282,7 @@ def make_stream(shape: "Shape | str", seq_id: int = 0, T: Optional[int] = None, 
     pod[ti, vi, si] = pi
     return Stream(sh, seq_id, rig, dets, counts, pod, gt,
                   dict(noise_px=noise_px, miss_prob=miss_prob, outlier_prob=outlier_prob,
-                       enter_stagger=enter_stagger))
+                       enter_stagger=enter_stagger, absences=list(absences)))
 
 
 def make_batch(shape: "Shape | str", n_seq: int, T: Optional[int] = None, seq0: int = 0, **kw):

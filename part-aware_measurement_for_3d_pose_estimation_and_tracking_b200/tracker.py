@@ -1,0 +1,200 @@
+"""Batched, device-resident tracker: S independent sequences x T frames per call.
+
+Thin host wrapper over the C ABI (``include/pam.h``): ``pam_track_sequences`` runs one CTA per
+sequence over all T frames with the tracker state (tracks, view lists, smoothed-pose history,
+velocities) resident in HBM; nothing returns to the host between frames.  torch is used only to own
+device memory and streams."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _capi, camera as _camera
+
+TENTATIVE, CONFIRMED, DELETED = 1, 2, 3
+
+
+class PamError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"libpam status {status}: {message}")
+        self.status = status
+
+
+def _check(lib, handle, rc):
+    if rc != 0:
+        msg = lib.pam_last_error(handle)
+        raise PamError(rc, (msg or b"").decode() or lib.pam_status_string(rc).decode())
+
+
+def _np_ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class SequenceTracker:
+    """``IterativeTracker`` semantics (src/tracking/IterativeTracker.py:34-180) for a batch of
+    independent sequences that share one camera rig."""
+
+    def __init__(self, cameras: Sequence, params, num_sequences: int = 1, max_detections: int = 8,
+                 max_tracks: int = 8, arm_joints: Sequence[int] = (9, 10), min_valid_joints: int = 10,
+                 device: int = 0):
+        self.lib = _capi.load_library()
+        self.cfg = _capi.make_config(params, len(cameras), max_detections, max_tracks, arm_joints, min_valid_joints)
+        self.S = int(num_sequences)
+        self.device = int(device)
+        self.handle = C.c_void_p()
+        rc = self.lib.pam_create(C.byref(self.cfg), self.device, C.byref(self.handle))
+        _check(self.lib, None, rc)
+        self._cam_arrays = _camera.pack_cameras(cameras)
+        _check(self.lib, self.handle, self.lib.pam_set_cameras(self.handle, *[_np_ptr(a) for a in self._cam_arrays]))
+        self.layout = _capi.PamStateLayout()
+        _check(self.lib, self.handle, self.lib.pam_get_state_layout(self.handle, C.byref(self.layout)))
+        self.next_frame = 0
+        self._state = None   # torch uint8 tensor on the device (device-pointer path)
+
+    # -- life-cycle ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.pam_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.pam_launch_count(self.handle))
+
+    def _torch(self):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("SequenceTracker needs a CUDA device (no CPU fallback)")
+        return torch
+
+    def restart(self):
+        """``track_restart`` for every sequence."""
+        torch = self._torch()
+        if self._state is None:
+            self._state = torch.empty(self.S * self.layout.seq_bytes, dtype=torch.uint8, device=f"cuda:{self.device}")
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _check(self.lib, self.handle, self.lib.pam_track_reset(self.handle, C.c_void_p(self._state.data_ptr()), self.S,
+                                                               C.c_void_p(st)))
+        self.next_frame = 0
+
+    # -- device-pointer path ------------------------------------------------------------------
+    def alloc_outputs(self, T: int, nviews: bool = True, assoc: bool = False):
+        torch = self._torch()
+        dev = f"cuda:{self.device}"
+        c = self.cfg
+        out = dict(count=torch.empty((self.S, T), dtype=torch.int32, device=dev),
+                   ids=torch.empty((self.S, T, c.max_tracks), dtype=torch.int32, device=dev),
+                   joints=torch.empty((self.S, T, c.max_tracks, c.num_joints, 3), dtype=torch.float32, device=dev))
+        out["nviews"] = torch.empty((self.S, T, c.max_tracks, c.num_joints), dtype=torch.uint8, device=dev) if nviews else None
+        out["assoc"] = torch.empty((self.S, T, c.num_cameras, c.max_detections), dtype=torch.int32, device=dev) if assoc else None
+        return out
+
+    def run(self, dets, counts, out: Optional[dict] = None, frame0: Optional[int] = None, nviews=True, assoc=False):
+        """``dets`` (S,T,V,D,J,3) float32 and ``counts`` (S,T,V) int32 CUDA tensors.  Asynchronous on
+        torch's current stream; returns the dict of output tensors."""
+        torch = self._torch()
+        c = self.cfg
+        S, T = dets.shape[0], dets.shape[1]
+        assert S == self.S and tuple(dets.shape[2:]) == (c.num_cameras, c.max_detections, c.num_joints, 3), dets.shape
+        assert dets.dtype == torch.float32 and counts.dtype == torch.int32 and dets.is_contiguous() and counts.is_contiguous()
+        assert dets.is_cuda and counts.is_cuda
+        if self._state is None:
+            self.restart()
+        if out is None:
+            out = self.alloc_outputs(T, nviews, assoc)
+        f0 = self.next_frame if frame0 is None else frame0
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        rc = self.lib.pam_track_sequences(self.handle, p(self._state), S, T, f0, p(dets), p(counts), p(out["count"]),
+                                          p(out["ids"]), p(out["joints"]), p(out.get("nviews")), p(out.get("assoc")),
+                                          C.c_void_p(st))
+        _check(self.lib, self.handle, rc)
+        self.next_frame = f0 + T
+        return out
+
+    def check(self):
+        """Synchronise and raise if any sequence overflowed a capacity limit."""
+        torch = self._torch()
+        status = np.zeros(self.S, np.int32)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.pam_track_status(self.handle, C.c_void_p(self._state.data_ptr()), self.S, _np_ptr(status), C.c_void_p(st))
+        _check(self.lib, self.handle, rc)
+        return status
+
+    # -- host-buffer path (what a reference-side caller would use) ------------------------------
+    def run_host(self, dets: np.ndarray, counts: np.ndarray, frame0: Optional[int] = None, fresh: bool = False,
+                 nviews: bool = True, assoc: bool = False, out: Optional[dict] = None):
+        """numpy in, numpy out through ``pam_track_sequences_host`` (H2D + kernel + D2H + sync)."""
+        c = self.cfg
+        dets = np.ascontiguousarray(dets, np.float32)
+        counts = np.ascontiguousarray(counts, np.int32)
+        S, T = dets.shape[0], dets.shape[1]
+        assert tuple(dets.shape[2:]) == (c.num_cameras, c.max_detections, c.num_joints, 3), dets.shape
+        if out is None:
+            out = dict(count=np.empty((S, T), np.int32), ids=np.empty((S, T, c.max_tracks), np.int32),
+                       joints=np.empty((S, T, c.max_tracks, c.num_joints, 3), np.float32),
+                       nviews=np.empty((S, T, c.max_tracks, c.num_joints), np.uint8) if nviews else None,
+                       assoc=np.empty((S, T, c.num_cameras, c.max_detections), np.int32) if assoc else None)
+        if fresh:
+            self.next_frame = 0
+        f0 = self.next_frame if frame0 is None else frame0
+        rc = self.lib.pam_track_sequences_host(self.handle, S, T, f0, 1 if fresh else 0, _np_ptr(dets), _np_ptr(counts),
+                                               _np_ptr(out["count"]), _np_ptr(out["ids"]), _np_ptr(out["joints"]),
+                                               _np_ptr(out.get("nviews")), _np_ptr(out.get("assoc")))
+        _check(self.lib, self.handle, rc)
+        self.next_frame = f0 + T
+        self._host_S = S
+        return out
+
+    # -- state read-back (IterTrack read surface) ---------------------------------------------
+    def read_state(self, host_path: bool = False):
+        """Parse the tracker state of every sequence: list (per sequence) of track dicts in
+        track-list order with the reference's IterTrack fields."""
+        L = self.layout
+        if host_path:
+            S = self._host_S
+            blob = np.empty(S * L.seq_bytes, np.uint8)
+            _check(self.lib, self.handle, self.lib.pam_track_state_to_host(self.handle, S, _np_ptr(blob)))
+        else:
+            S = self.S
+            self._torch().cuda.synchronize(self.device)
+            blob = self._state.cpu().numpy()
+        return parse_state(blob, S, L, self.cfg)
+
+
+def parse_state(blob: np.ndarray, S: int, L, cfg):
+    J, V, MT, H = cfg.num_joints, cfg.num_cameras, cfg.max_tracks, L.hist_ring
+    seqs = []
+    for s in range(S):
+        base = blob[s * L.seq_bytes:(s + 1) * L.seq_bytes]
+        hdr = base[L.off_header:L.off_header + 4 * (5 + L.max_order)].view(np.int32)
+        ntracks, next_id, status = int(hdr[0]), int(hdr[1]), int(hdr[2])
+        order = hdr[5:5 + ntracks]
+        meta = base[L.off_meta:L.off_meta + 4 * L.meta_ints * MT].view(np.int32).reshape(MT, L.meta_ints)
+        hist = base[L.off_hist:L.off_hist + 8 * MT * H * J * 3].view(np.float64).reshape(MT, H, J, 3)
+        view = base[L.off_view:L.off_view + 4 * MT * V * J * 3].view(np.float32).reshape(MT, V, J, 3)
+        vel = base[L.off_vel:L.off_vel + 4 * MT * J * 3].view(np.float32).reshape(MT, J, 3)
+        nv = base[L.off_nviews:L.off_nviews + MT * J].reshape(MT, J)
+        tracks = []
+        for slot in order:
+            m = meta[slot]
+            nviews, hs, hl = int(m[6]), int(m[7]), int(m[8])
+            vc = m[9:9 + L.max_views]
+            vt = m[9 + L.max_views:9 + 2 * L.max_views]
+            ht = m[9 + 2 * L.max_views:9 + 2 * L.max_views + H]
+            poses2d = {int(vc[k]): dict(time=int(vt[k]), pose=view[slot, k].astype(np.float64)) for k in range(nviews)}
+            ring = [(hs + i) % H for i in range(hl)]
+            poses3d = [dict(time=int(ht[r]), pose3d=hist[slot, r].copy()) for r in ring]
+            tracks.append(dict(track_id=int(m[0]), hits=int(m[1]), age=int(m[2]), time_since_update=int(m[3]),
+                               state=int(m[4]), already_update=bool(m[5]), poses2d=poses2d, poses3d=poses3d,
+                               velocity_3d=vel[slot].copy(), joint_views=nv[slot].copy()))
+        seqs.append(dict(tracks=tracks, next_id=next_id, status=status))
+    return seqs

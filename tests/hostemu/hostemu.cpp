@@ -1,0 +1,62 @@
+// TEST / DEBUG INFRASTRUCTURE ONLY.
+// Compiles the block-cooperative tracker source (csrc/pam_track.h) for the HOST with a single
+// "thread" so that the algorithmic logic of the CUDA kernel can be checked against the oracle in
+// the GPU-less build container.  It is built by tests/hostemu/build.py into tests/hostemu/_build/,
+// is loaded only by tests/ (-m "not gpu"), and is never imported, linked or shipped by the
+// package: the product path is libpam.so and fails loudly without a GPU.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../part-aware_measurement_for_3d_pose_estimation_and_tracking_b200/csrc/pam_host.h"
+
+using namespace pam;
+
+extern "C" int hostemu_track_sequences(const pam_config* cfg, const float* P, const float* RKinv, const double* pos,
+                                       const float* F, int S, int T, int frame0, const float* dets,
+                                       const int32_t* counts, int32_t* out_count, int32_t* out_ids,
+                                       float* out_joints, uint8_t* out_nviews, int32_t* out_assoc,
+                                       int32_t* status, void* state_io /* may be null; S*seq_bytes, zero = fresh */) {
+    DevCfg c;
+    std::string err;
+    int rc = make_devcfg(*cfg, c, err);
+    if (rc != PAM_OK) return rc;
+    std::vector<char> own;
+    char* state = (char*)state_io;
+    if (!state) { own.assign((size_t)c.seq_bytes * S, 0); state = own.data(); }
+    std::vector<double> arena((size_t)arena_doubles(c));
+    SeqShared* sh = new SeqShared();
+    HostCtx ctx;
+    CamConst cc{P, RKinv, pos, F};
+    const int64_t fstride = (int64_t)c.V * c.D * c.J * 3;
+    for (int s = 0; s < S; ++s) {
+        std::memset((void*)sh, 0, sizeof(SeqShared));
+        carve(c, *sh, arena.data());
+        SeqGlobal g;
+        g.bind(c, state + (int64_t)s * c.seq_bytes);
+        load_cameras(ctx, c, *sh, cc);
+        load_state(ctx, c, *sh, g);
+        for (int t = 0; t < T; ++t) {
+            const int64_t ft = (int64_t)s * T + t;
+            FrameOut o;
+            o.count = out_count + ft;
+            o.ids = out_ids ? out_ids + ft * c.max_trk : nullptr;
+            o.joints = out_joints ? out_joints + ft * c.max_trk * c.J * 3 : nullptr;
+            o.nviews = out_nviews ? out_nviews + ft * c.max_trk * c.J : nullptr;
+            o.assoc = out_assoc ? out_assoc + ft * c.V * c.D : nullptr;
+            frame_step(ctx, c, *sh, g, frame0 + t, dets + ft * fstride, counts + ft * c.V, o);
+        }
+        store_state(ctx, c, *sh, g);
+        if (status) status[s] = sh->hdr.status;
+    }
+    delete sh;
+    return PAM_OK;
+}
+
+extern "C" int hostemu_state_layout(const pam_config* cfg, pam_state_layout* L) {
+    DevCfg c;
+    std::string err;
+    int rc = make_devcfg(*cfg, c, err);
+    if (rc != PAM_OK) return rc;
+    fill_layout(c, *L);
+    return PAM_OK;
+}
