@@ -84,7 +84,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("PAM_LIBRARY") or LIB_PATH   # PAM_LIBRARY: development builds (phase timing)
     if not os.path.exists(p):
         raise RuntimeError(f"libpam.so not found at {p}: build it with __graft_entry__.build(); "
                            "this package has no CPU fallback")

@@ -92,36 +92,32 @@ struct NpSumStream {
 // ------------------------------------------------------------------------------------------
 // F is the 3x3 (row-major) fundamental matrix cams[a].F[cid_b]:  x_a^T F x_b = 0,  x = (u, v, 1).
 
-// float64 form of utils/matching.py:136-146: line l = F^T x_a in image b, normalised by
-// ||l[:2]|| (0 -> 1), distance |l . x_b| / sqrt(l0^2 + l1^2).
+// Reciprocal square root: one MUFU.RSQ64H seed + Newton steps on the device (cheaper than a
+// divide plus a square root), 1/sqrt on the host harness.
+PAM_HD double rsqrt_f64(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+// float64 form of utils/matching.py:136-146: line l = F^T x_a in image b, distance of x_b to it.
+// The reference normalises l by ||l[:2]|| (0 -> 1) and then divides by sqrt(l0^2 + l1^2) = 1 again;
+// here both collapse into one reciprocal square root (differs by rounding only).
 PAM_HD double epi_dist_f64(const double* F, double ua, double va, double ub, double vb) {
     double l0 = F[0] * ua + F[3] * va + F[6];
     double l1 = F[1] * ua + F[4] * va + F[7];
     double l2 = F[2] * ua + F[5] * va + F[8];
-    double nu = sqrt(l0 * l0 + l1 * l1);
-    if (nu == 0.0) nu = 1.0;
-    l0 /= nu; l1 /= nu; l2 /= nu;
-    double nn = l0 * l0 + l1 * l1;
-    if (nn == 0.0) nn = 1.0;
-    return fabs(ub * l0 + vb * l1 + l2) / sqrt(nn);
-}
-
-// same with the transposed matrix: line l = F x_b in image a, distance of x_a to it
-PAM_HD double epi_dist_f64_T(const double* F, double ub, double vb, double ua, double va) {
-    double l0 = F[0] * ub + F[1] * vb + F[2];
-    double l1 = F[3] * ub + F[4] * vb + F[5];
-    double l2 = F[6] * ub + F[7] * vb + F[8];
-    double nu = sqrt(l0 * l0 + l1 * l1);
-    if (nu == 0.0) nu = 1.0;
-    l0 /= nu; l1 /= nu; l2 /= nu;
-    double nn = l0 * l0 + l1 * l1;
-    if (nn == 0.0) nn = 1.0;
-    return fabs(ua * l0 + va * l1 + l2) / sqrt(nn);
+    double n2 = l0 * l0 + l1 * l1;
+    double inv = (n2 == 0.0) ? 1.0 : rsqrt_f64(n2);
+    return fabs(ub * l0 + vb * l1 + l2) * inv;
 }
 
 // cv::computeCorrespondEpilines arithmetic (double path): (a,b,c) = M x, nu = a^2+b^2,
-// nu = nu ? 1/sqrt(nu) : 1, scaled;  then utils/matching.py:82-83:
-// |x . l| / sqrt(l0^2 + l1^2).   transposed = false: M = F ;  true: M = F^T.
+// nu = nu ? 1/sqrt(nu) : 1, scaled;  then utils/matching.py:82-83: |x . l| / sqrt(l0^2 + l1^2)
+// (= 1 after the scaling; for nu == 0 the reference divides by 0 and so does this).
+// transposed = false: M = F ;  true: M = F^T.
 PAM_HD double epi_dist_cv(const double* F, bool transposed, double xs, double ys, double xt, double yt) {
     double a, b, c;
     if (!transposed) {
@@ -133,10 +129,8 @@ PAM_HD double epi_dist_cv(const double* F, bool transposed, double xs, double ys
         b = F[1] * xs + F[4] * ys + F[7];
         c = F[2] * xs + F[5] * ys + F[8];
     }
-    double nu = a * a + b * b;
-    nu = (nu != 0.0) ? 1.0 / sqrt(nu) : 1.0;
-    a *= nu; b *= nu; c *= nu;
-    return fabs(xt * a + yt * b + c) / sqrt(a * a + b * b);
+    double n2 = a * a + b * b;
+    return fabs(xt * a + yt * b + c) * rsqrt_f64(n2);
 }
 
 // epipolar_distance(cam1, person1, cam2, person2)[j] = [d1, d2] with F = cam1.F[cam2.cid]:
@@ -149,39 +143,57 @@ PAM_HD void epi_pair_cv(const double* F12, double u1, double v1, double u2, doub
 // ------------------------------------------------------------------------------------------
 // back-projected ray to 3-D point distance
 // ------------------------------------------------------------------------------------------
-// RK = R^-1 K^-1 (row-major 3x3), pos = camera centre, (u, v) pixel, X = 3-D point.
+// RK = R^-1 K^-1 (row-major 3x3), pos = camera centre, (u, v) pixel, X = 3-D point:
+// || dir x (pos - X) || / || dir ||   (utils/matching.py:10-17 + utils/calculate.py:26-32; the
+// reference normalises dir first and re-derives it as (pos + dir) - pos, a rounding-level detail).
 PAM_HD double ray_point_distance(const double* RK, const double* pos, double u, double v, const double* X) {
-    double d0 = RK[0] * u + RK[1] * v + RK[2];
-    double d1 = RK[3] * u + RK[4] * v + RK[5];
-    double d2 = RK[6] * u + RK[7] * v + RK[8];
-    double nrm = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-    d0 /= nrm; d1 /= nrm; d2 /= nrm;
-    // x2 - x1 with x2 = pos + dir, as the reference forms it (utils/calculate.py:29-30)
-    double a0 = (pos[0] + d0) - pos[0], a1 = (pos[1] + d1) - pos[1], a2 = (pos[2] + d2) - pos[2];
+    double a0 = RK[0] * u + RK[1] * v + RK[2];
+    double a1 = RK[3] * u + RK[4] * v + RK[5];
+    double a2 = RK[6] * u + RK[7] * v + RK[8];
     double b0 = pos[0] - X[0], b1 = pos[1] - X[1], b2 = pos[2] - X[2];
     double c0 = a1 * b2 - a2 * b1;
     double c1 = a2 * b0 - a0 * b2;
     double c2 = a0 * b1 - a1 * b0;
-    return sqrt(c0 * c0 + c1 * c1 + c2 * c2) / sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+    return sqrt((c0 * c0 + c1 * c1 + c2 * c2) / (a0 * a0 + a1 * a1 + a2 * a2));
 }
 
 // ------------------------------------------------------------------------------------------
 // triangulation: weighted homogeneous DLT
 // ------------------------------------------------------------------------------------------
-// Upper-triangular 4x4 factor R (10 entries) of the stacked rows, built row by row with Givens
-// rotations, so the system never has to exist in memory whatever the number of views.
+// The reference stacks the 2k weighted unit rows of the k surviving views and takes the right
+// singular vector of the smallest singular value (la.svd, utils/construction.py:109-113).  Here the
+// system never exists in memory: rows are folded, as they are produced, into the 10 entries of the
+// upper-triangular 4x4 factor R with A^T A = R^T R, and the singular vector is extracted from R.
+//
+//   fold      fresh views only (all weights 1):  Gram matrix + Cholesky      (10 FMA per row)
+//             any stale view (weights e^{-lambda_t T} down to 3e-7):  streaming Givens QR, which
+//             keeps the relative accuracy of the tiny rows that a Gram matrix would lose
+//   extract   inverse iteration with R (two triangular solves per step, converges like
+//             (sigma4/sigma3)^2); if it has not settled in 8 steps, or a pivot is degenerate,
+//             one-sided Jacobi SVD of R (unconditionally robust)
 struct DltAccum {
-    double r00, r01, r02, r03, r11, r12, r13, r22, r23, r33;
-    PAM_HD void reset() { r00 = r01 = r02 = r03 = r11 = r12 = r13 = r22 = r23 = r33 = 0.0; }
+    double r00, r01, r02, r03, r11, r12, r13, r22, r23, r33;   // Gram entries, then R
+    bool gram;
+
+    PAM_HD void reset(bool use_gram) {
+        r00 = r01 = r02 = r03 = r11 = r12 = r13 = r22 = r23 = r33 = 0.0;
+        gram = use_gram;
+    }
 
     PAM_HD static void givens(double& d, double& x, double& c, double& s) {
-        // rotate (d, x) -> (r, 0); c, s from a reciprocal square root
         double h2 = d * d + x * x;
-        double inv = 1.0 / sqrt(h2);
+        double inv = rsqrt_f64(h2);
         c = d * inv; s = x * inv;
         d = h2 * inv; x = 0.0;
     }
     PAM_HD void add_row(double x0, double x1, double x2, double x3) {
+        if (gram) {
+            r00 += x0 * x0; r01 += x0 * x1; r02 += x0 * x2; r03 += x0 * x3;
+            r11 += x1 * x1; r12 += x1 * x2; r13 += x1 * x3;
+            r22 += x2 * x2; r23 += x2 * x3;
+            r33 += x3 * x3;
+            return;
+        }
         double c, s, t;
         if (x0 != 0.0) {
             givens(r00, x0, c, s);
@@ -206,19 +218,75 @@ struct DltAccum {
     //   (u P2 - P0)/||.|| * w ,  (v P2 - P1)/||.|| * w      with P row-major 3x4
     PAM_HD void add_view(const double* P, double u, double v, double w) {
         double a0 = u * P[8] - P[0], a1 = u * P[9] - P[1], a2 = u * P[10] - P[2], a3 = u * P[11] - P[3];
-        double na = sqrt(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3);
-        add_row(a0 / na * w, a1 / na * w, a2 / na * w, a3 / na * w);
+        double sa = w * rsqrt_f64(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3);
+        add_row(a0 * sa, a1 * sa, a2 * sa, a3 * sa);
         double b0 = v * P[8] - P[4], b1 = v * P[9] - P[5], b2 = v * P[10] - P[6], b3 = v * P[11] - P[7];
-        double nb = sqrt(b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3);
-        add_row(b0 / nb * w, b1 / nb * w, b2 / nb * w, b3 / nb * w);
+        double sb = w * rsqrt_f64(b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3);
+        add_row(b0 * sb, b1 * sb, b2 * sb, b3 * sb);
     }
 
-    // Right singular vector of the smallest singular value by one-sided (Hestenes) Jacobi on
-    // the columns of R; de-homogenised into X[3].  Replaces la.svd at utils/construction.py:110-113.
-    PAM_HD void solve(double* X) const {
+    // Gram -> R in place.  false when a pivot is too small for the squared system to be trusted.
+    PAM_HD bool cholesky() {
+        const double g11 = r11, g22 = r22, g33 = r33;
+        if (!(r00 > 0.0)) return false;
+        double i0 = rsqrt_f64(r00);
+        r00 *= i0; r01 *= i0; r02 *= i0; r03 *= i0;
+        double t11 = r11 - r01 * r01;
+        if (!(t11 > 1e-9 * g11)) return false;
+        double i1 = rsqrt_f64(t11);
+        r11 = t11 * i1;
+        r12 = (r12 - r01 * r02) * i1;
+        r13 = (r13 - r01 * r03) * i1;
+        double t22 = r22 - r02 * r02 - r12 * r12;
+        if (!(t22 > 1e-9 * g22)) return false;
+        double i2 = rsqrt_f64(t22);
+        r22 = t22 * i2;
+        r23 = (r23 - r02 * r03 - r12 * r13) * i2;
+        double t33 = r33 - r03 * r03 - r13 * r13 - r23 * r23;
+        if (!(t33 > 1e-13 * g33)) return false;
+        r33 = t33 * rsqrt_f64(t33);
+        return true;
+    }
+
+    // inverse iteration on R^T R; x = homogeneous solution (unit norm).  false = not converged.
+    PAM_HD bool invit(double* x) const {
+        if (r00 == 0.0 || r11 == 0.0 || r22 == 0.0 || r33 == 0.0) return false;
+        const double i0 = 1.0 / r00, i1 = 1.0 / r11, i2 = 1.0 / r22, i3 = 1.0 / r33;
+        // start from R^-1 e4 (the direction R shrinks most when r33 is its smallest pivot)
+        double x3 = 1.0;
+        double x2 = -(r23 * x3) * i2;
+        double x1 = -(r12 * x2 + r13 * x3) * i1;
+        double x0 = -(r01 * x1 + r02 * x2 + r03 * x3) * i0;
+        double inv = rsqrt_f64(x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3);
+        x0 *= inv; x1 *= inv; x2 *= inv; x3 *= inv;
+        bool ok = false;
+        for (int it = 0; it < 8; ++it) {
+            double y0 = x0 * i0;
+            double y1 = (x1 - r01 * y0) * i1;
+            double y2 = (x2 - r02 * y0 - r12 * y1) * i2;
+            double y3 = (x3 - r03 * y0 - r13 * y1 - r23 * y2) * i3;
+            double z3 = y3 * i3;
+            double z2 = (y2 - r23 * z3) * i2;
+            double z1 = (y1 - r12 * z2 - r13 * z3) * i1;
+            double z0 = (y0 - r01 * z1 - r02 * z2 - r03 * z3) * i0;
+            inv = rsqrt_f64(z0 * z0 + z1 * z1 + z2 * z2 + z3 * z3);
+            if (z0 * x0 + z1 * x1 + z2 * x2 + z3 * x3 < 0.0) inv = -inv;
+            z0 *= inv; z1 *= inv; z2 *= inv; z3 *= inv;
+            double e0 = z0 - x0, e1 = z1 - x1, e2 = z2 - x2, e3 = z3 - x3;
+            x0 = z0; x1 = z1; x2 = z2; x3 = z3;
+            if (e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3 <= 1e-26) { ok = true; break; }
+        }
+        x[0] = x0; x[1] = x1; x[2] = x2; x[3] = x3;
+        return ok;
+    }
+
+    // One-sided (Hestenes) Jacobi on the columns of R: right singular vectors accumulate in V.
+    // Columns are orthogonalised to |g_p . g_q| <= 1e-14 |g_p||g_q| (a relative criterion, so the
+    // tiny singular values of stale-view systems are resolved as well as the large ones).
+    PAM_HD_NOINLINE void jacobi(double* x) const {
         double g[4][4] = {{r00, r01, r02, r03}, {0.0, r11, r12, r13}, {0.0, 0.0, r22, r23}, {0.0, 0.0, 0.0, r33}};
         double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
-        for (int sweep = 0; sweep < 12; ++sweep) {
+        for (int sweep = 0; sweep < 10; ++sweep) {
             bool rotated = false;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -237,12 +305,13 @@ struct DltAccum {
                         be += g[k][q] * g[k][q];
                         ga += g[k][p] * g[k][q];
                     }
-                    if (ga == 0.0 || fabs(ga) <= 1e-17 * sqrt(al * be)) continue;
+                    if (ga * ga <= 1e-28 * (al * be)) continue;
                     rotated = true;
-                    double zeta = (be - al) / (2.0 * ga);
-                    double t = 1.0 / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    if (zeta < 0.0) t = -t;
-                    double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                    // tan of the rotation angle: t = sign(tau) 2 ga / (|tau| + sqrt(tau^2 + 4 ga^2)), tau = be - al
+                    double tau = be - al, g2 = 2.0 * ga;
+                    double h = sqrt(tau * tau + g2 * g2);
+                    double t = g2 / ((tau < 0.0) ? (tau - h) : (tau + h));
+                    double c = rsqrt_f64(1.0 + t * t), s = c * t;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -267,13 +336,27 @@ struct DltAccum {
             double nq = g[0][q] * g[0][q] + g[1][q] * g[1][q] + g[2][q] * g[2][q] + g[3][q] * g[3][q];
             if (q == 0 || nq < best) { best = nq; arg = q; }
         }
-        double x0 = 0, x1 = 0, x2 = 0, x3 = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int q = 0; q < 4; ++q)
-            if (q == arg) { x0 = V[0][q]; x1 = V[1][q]; x2 = V[2][q]; x3 = V[3][q]; }
-        X[0] = x0 / x3; X[1] = x1 / x3; X[2] = x2 / x3;
+            if (q == arg) { x[0] = V[0][q]; x[1] = V[1][q]; x[2] = V[2][q]; x[3] = V[3][q]; }
+    }
+
+    // de-homogenised joint.  `path` (optional) reports which extractor produced it (tests).
+    PAM_HD void solve(double* X, int* path = nullptr) {
+        double x[4];
+        int how = 0;
+        if (gram && !cholesky()) {
+            // a squared system this close to singular is not trusted: signal the caller to refold
+            X[0] = X[1] = X[2] = 0.0;
+            if (path) *path = -1;
+            return;
+        }
+        if (!invit(x)) { jacobi(x); how = 1; }
+        double ix = 1.0 / x[3];
+        X[0] = x[0] * ix; X[1] = x[1] * ix; X[2] = x[2] * ix;
+        if (path) *path = how;
     }
 };
 

@@ -38,7 +38,39 @@ struct DeviceCtx {
         __syncthreads();
 #endif
     }
+    __host__ __device__ __forceinline__ void atomic_inc(int* p) const {
+#ifdef __CUDA_ARCH__
+        atomicAdd(p, 1);
+#else
+        *p += 1;
+#endif
+    }
 };
+
+// Asynchronous global -> shared staging of one frame's detections (LDGSTS / cp.async): issued for
+// frame t+1 while frame t is being processed, so the frame-serial chain never waits on HBM.
+__device__ __forceinline__ void stage_frame(float* sdst, int* scnt, const float* gsrc, const int* gcnt, int nfloats,
+                                            int V) {
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(sdst);
+    if ((nfloats & 3) == 0 && ((uintptr_t)gsrc & 15) == 0) {
+        for (int i = threadIdx.x; i < nfloats / 4; i += blockDim.x)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + i * 16), "l"(gsrc + i * 4) : "memory");
+    } else {
+        for (int i = threadIdx.x; i < nfloats; i += blockDim.x)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbase + i * 4), "l"(gsrc + i) : "memory");
+    }
+    const unsigned cbase = (unsigned)__cvta_generic_to_shared(scnt);
+    for (int i = threadIdx.x; i < V; i += blockDim.x)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cbase + i * 4), "l"(gcnt + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// dynamic shared memory of k_track_sequences: [arena doubles][2 x frame floats][2 x V counts]
+static inline size_t frame_floats_padded(const DevCfg& c) { return ((size_t)c.V * c.D * c.J * 3 + 3) / 4 * 4; }
+static inline size_t track_smem_bytes(const DevCfg& c) {
+    return (size_t)arena_doubles(c) * 8 + 2 * frame_floats_padded(c) * 4 + 2 * PAM_MAX_V * 4;
+}
 
 struct TrackIO {
     const float* dets;      // [S][T][V][D][J][3]
@@ -60,12 +92,26 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
     const int s = blockIdx.x;
     SeqGlobal g;
     g.bind(c, state + (int64_t)s * c.seq_bytes);
+    const int nfl = c.V * c.D * c.J * 3;
+    const int nfl_pad = (nfl + 3) / 4 * 4;
+    float* dbuf = (float*)(arena + arena_doubles(c));
+    int* cbuf = (int*)(dbuf + 2 * nfl_pad);
+    const float* gd = io.dets + (int64_t)s * T * nfl;
+    const int* gc = io.counts + (int64_t)s * T * c.V;
+    if (T > 0) stage_frame(dbuf, cbuf, gd, gc, nfl, c.V);
     if (threadIdx.x == 0) carve(c, sh, arena);
     load_cameras(ctx, c, sh, cc);
     load_state(ctx, c, sh, g);
+    stage_wait();
     __syncthreads();
-    const int64_t fstride = (int64_t)c.V * c.D * c.J * 3;
+#if defined(PAM_PHASE_TIMING)
+    if (threadIdx.x == 0) { for (int k = 0; k < 24; ++k) sh.phase_cyc[k] = 0; sh.tlast = clock64(); }
+#endif
     for (int t = 0; t < T; ++t) {
+        const int cur = t & 1;
+        if (t + 1 < T)
+            stage_frame(dbuf + (cur ^ 1) * nfl_pad, cbuf + (cur ^ 1) * PAM_MAX_V, gd + (int64_t)(t + 1) * nfl,
+                        gc + (t + 1) * c.V, nfl, c.V);
         const int64_t ft = (int64_t)s * T + t;
         FrameOut o;
         o.count = io.out_count ? io.out_count + ft : nullptr;
@@ -73,9 +119,23 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
         o.joints = io.out_joints ? io.out_joints + ft * c.max_trk * c.J * 3 : nullptr;
         o.nviews = io.out_nv ? io.out_nv + ft * c.max_trk * c.J : nullptr;
         o.assoc = io.out_assoc ? io.out_assoc + ft * c.V * c.D : nullptr;
-        frame_step(ctx, c, sh, g, frame0 + t, io.dets + ft * fstride, io.counts + ft * c.V, o);
+        frame_step(ctx, c, sh, g, frame0 + t, dbuf + cur * nfl_pad, cbuf + cur * PAM_MAX_V, o);
+        stage_wait();
+        __syncthreads();
+        PAM_MARK(8);
     }
     store_state(ctx, c, sh, g);
+#if defined(PAM_PHASE_TIMING)
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        static const char* nm[9] = {"1 age+reproj", "2 affinity", "3 assign", "4 add_pose+believe", "5 filter+dlt",
+                                    "6 smooth+motion+out", "7 lifecycle+reap", "8 init", "9 stage wait"};
+        long long tot = 0;
+        for (int k = 0; k < 9; ++k) tot += sh.phase_cyc[k];
+        for (int k = 0; k < 9; ++k)
+            printf("phase %-22s %9.0f cyc/frame %5.1f%%\n", nm[k], (double)sh.phase_cyc[k] / T, 100.0 * sh.phase_cyc[k] / tot);
+        printf("total %.0f cyc/frame\n", (double)tot / T);
+    }
+#endif
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -226,7 +286,7 @@ int pam_track_sequences(pam_handle* h, void* d_state, int32_t S, int32_t T, int3
     if (!h->have_cameras) return fail(h, PAM_E_NOCAMERAS, "pam_set_cameras has not been called");
     if (S == 0 || T == 0) return PAM_OK;
     CK(cudaSetDevice(h->device));
-    const size_t smem = (size_t)arena_doubles(h->dc) * sizeof(double);
+    const size_t smem = track_smem_bytes(h->dc);
     if (smem > 48 * 1024 - sizeof(SeqShared))
         CK(cudaFuncSetAttribute(k_track_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TrackIO io{d_dets, d_counts, d_out_count, d_out_ids, d_out_joints, d_out_nviews, d_out_assoc};

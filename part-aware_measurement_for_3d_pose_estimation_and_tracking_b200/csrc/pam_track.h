@@ -104,15 +104,17 @@ struct SeqShared {
     int n;                                   // tracks alive at frame start
     int m[PAM_MAX_V];                        // detections per camera
     int dt[PAM_MAX_TRK];
+    double inv_denom[PAM_MAX_TRK];           // 1 / (alpha2d * dt)
+    double inv_decay[PAM_MAX_TRK];           // 1 / exp(lambda_a * dt)
     int last[PAM_MAX_TRK];                   // ring index of the last pose
-    int newpos[PAM_MAX_TRK];                 // ring index the new pose goes to
     signed char t2d[PAM_MAX_V][PAM_MAX_TRK];
     signed char d2t[PAM_MAX_V][PAM_MAX_D];
     signed char vk[PAM_MAX_V][PAM_MAX_TRK];  // view slot written by add_pose
     signed char gv_idx[PAM_MAX_TRK][PAM_MAX_V];
     int gv_n[PAM_MAX_TRK];
     int do_update[PAM_MAX_TRK];
-    int ok[PAM_MAX_TRK];
+    int fail[PAM_MAX_TRK];                   // joints left with < 2 views
+    int conflict[PAM_MAX_V];                 // camera needs the full assignment solver
     unsigned char nvj[PAM_MAX_TRK][PAM_MAX_J];
     // init
     double believe[PAM_MAX_V][PAM_MAX_D];
@@ -132,6 +134,10 @@ struct SeqShared {
     // output
     int out_n;
     signed char out_slot[PAM_MAX_TRK];
+#if defined(PAM_PHASE_TIMING)
+    long long phase_cyc[24];
+    long long tlast;
+#endif
     // arena pointers (set by carve())
     double* aff;      // [V][max_trk][D]
     double* reproj;   // [V][max_trk][J][2]   (v, u)
@@ -159,7 +165,22 @@ struct HostCtx {
     inline int tid() const { return 0; }
     inline int nthreads() const { return 1; }
     inline void sync() const {}
+    inline void atomic_inc(int* p) const { *p += 1; }
 };
+
+// optional per-phase cycle accounting (development builds: -DPAM_PHASE_TIMING, device only)
+#if defined(PAM_PHASE_TIMING) && defined(__CUDA_ARCH__)
+#define PAM_MARK(k)                                                        \
+    do {                                                                   \
+        if (ctx.tid() == 0) {                                              \
+            long long _t = clock64();                                      \
+            sh.phase_cyc[k] += _t - sh.tlast;                              \
+            sh.tlast = _t;                                                 \
+        }                                                                  \
+    } while (0)
+#else
+#define PAM_MARK(k) do { } while (0)
+#endif
 
 #define PAM_FOR(i, N) for (int i = ctx.tid(), _n_##i = (N), _s_##i = ctx.nthreads(); i < _n_##i; i += _s_##i)
 
@@ -203,6 +224,28 @@ PAM_HD void store_state(Ctx& ctx, const DevCfg& c, const SeqShared& sh, const Se
 // per-joint pieces of the update / init paths
 // ------------------------------------------------------------------------------------------
 
+// Weighted DLT over the surviving views (bit a of `alive`); T == nullptr means all ages 0.
+// Fresh-only systems go through the Gram/Cholesky fold; if that is judged too close to singular
+// (or any view is stale) the rows are folded again with Givens rotations.
+template <class CidT>
+PAM_HD void dlt_from_views(const DevCfg& c, const SeqShared& sh, int Vt, const CidT* cid, const int* T,
+                           const double* u, const double* v, uint32_t alive, bool fresh, double* X) {
+    DltAccum acc;
+    int path = -1;
+    if (fresh) {
+        acc.reset(true);
+        for (int a = 0; a < Vt; ++a)
+            if ((alive >> a) & 1u) acc.add_view(sh.P[cid[a]], u[a], v[a], c.w_age[0]);
+        acc.solve(X, &path);
+    }
+    if (path < 0) {
+        acc.reset(false);
+        for (int a = 0; a < Vt; ++a)
+            if ((alive >> a) & 1u) acc.add_view(sh.P[cid[a]], u[a], v[a], c.w_age[T ? T[a] : 0]);
+        acc.solve(X, &path);
+    }
+}
+
 // Part-aware view filter + DLT for one joint of one track (update mode).
 //   views 0..Vt-1 in the track's dict order; cid/T per view; (u, v) per view; next = predicted joint.
 // Returns the number of surviving views; X = triangulated joint (or `next` when < 2 views).
@@ -238,11 +281,10 @@ PAM_HD int joint_update(const DevCfg& c, const SeqShared& sh, int Vt, const int*
         X[0] = next[0]; X[1] = next[1]; X[2] = next[2];
         return nv;
     }
-    DltAccum acc;
-    acc.reset();
+    bool fresh = true;
     for (int a = 0; a < Vt; ++a)
-        if ((alive >> a) & 1u) acc.add_view(sh.P[cid[a]], u[a], v[a], c.w_age[T[a]]);
-    acc.solve(X);
+        if (((alive >> a) & 1u) && T[a] != 0) fresh = false;
+    dlt_from_views(c, sh, Vt, cid, T, u, v, alive, fresh, X);
     return nv;
 }
 
@@ -275,11 +317,7 @@ PAM_HD int joint_init(const DevCfg& c, const SeqShared& sh, int Vt, const signed
     int nv = 0;
     for (int a = 0; a < Vt; ++a) nv += (alive >> a) & 1u;
     if (nv < 2) return nv;
-    DltAccum acc;
-    acc.reset();
-    for (int a = 0; a < Vt; ++a)
-        if ((alive >> a) & 1u) acc.add_view(sh.P[cid[a]], u[a], v[a], c.w_age[0]);
-    acc.solve(X);
+    dlt_from_views(c, sh, Vt, cid, (const int*)nullptr, u, v, alive, true, X);
     return nv;
 }
 
@@ -312,6 +350,20 @@ PAM_HD double hyp_cost(const DevCfg& c, const SeqShared& sh, const float* dets, 
 // ------------------------------------------------------------------------------------------
 // the frame
 // ------------------------------------------------------------------------------------------
+// per-track success test of update_3dpose (IterativeTracker.py:324-325, 369), valid after phase 5
+PAM_HD bool track_ok(const DevCfg& c, const SeqShared& sh, int i) {
+    return sh.do_update[i] && !((double)sh.fail[i] > c.fail_limit) &&
+           sh.trk[sh.hdr.order[i]].hist_len < PAM_HIST;
+}
+// will track i be reported this frame (Confirmed after this update, ivclabpose.py:266)?
+PAM_HD bool track_reported(const DevCfg& c, const SeqShared& sh, int i) {
+    if (!track_ok(c, sh, i)) return false;
+    const TrkMeta& t = sh.trk[sh.hdr.order[i]];
+    return t.state == ST_CONFIRMED || (t.state == ST_TENTATIVE && t.hits + 1 >= c.n_init);
+}
+
+// `dets`/`counts` point at this frame's detections (staged in shared memory by the kernel).
+// The caller must synchronise the block after frame_step returns.
 template <class Ctx>
 PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal& g, int frame,
                        const float* dets /* [V][D][J][3] */, const int* counts /* [V] */, const FrameOut& out) {
@@ -321,122 +373,160 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         if (ctx.tid() == 0 && out.count) *out.count = 0;
         return;
     }
-
-    // ---- phase 0: ageing + snapshot (IterativeTracker.py:126-129) ------------------------------
     const int n = sh.hdr.ntracks;
+
+    // ---- phase 1: ageing + snapshot (IterativeTracker.py:126-129) and reprojection of every track
+    //      joint into every camera (ivclabpose.py:91-98) ------------------------------------------
     PAM_FOR(i, n) {
         TrkMeta& t = sh.trk[sh.hdr.order[i]];
         t.already = 0; t.age += 1; t.tsu += 1;
-        int last = (t.hist_start + t.hist_len - 1) % PAM_HIST;
+        const int last = (t.hist_start + t.hist_len - 1) % PAM_HIST;
+        const int dt = frame - t.hist_time[last];
         sh.last[i] = last;
-        sh.dt[i] = frame - t.hist_time[last];
+        sh.dt[i] = dt;
+        sh.inv_denom[i] = 1.0 / (c.alpha2d * (double)dt);          // IterativeTracker.py:143
+        sh.inv_decay[i] = 1.0 / exp(c.lambda_a * (double)dt);      // IterativeTracker.py:148
+        sh.fail[i] = 0;
     }
     PAM_FOR(cc, V) {
         int mm = counts[cc];
         if (mm > D || mm < 0) { sh.hdr.status = SEQ_ERR_DET_OVERFLOW; mm = 0; }
         sh.m[cc] = mm;
+        sh.conflict[cc] = 0;
     }
     PAM_FOR(i, V * MT) sh.t2d[i / MT][i % MT] = -1;
     PAM_FOR(i, V * D) sh.d2t[i / D][i % D] = -1;
-    ctx.sync();
-
-    if (n > 0) {
-        // ---- phase 1: reprojection of every track joint into every camera (ivclabpose.py:91-98)
-        PAM_FOR(it, V * n * J) {
-            const int cam = it / (n * J), i = (it / J) % n, j = it % J;
-            if (sh.m[cam] == 0) continue;
-            const double* X = g.hist + ((int64_t)(sh.hdr.order[i] * PAM_HIST + sh.last[i]) * J + j) * 3;
+    PAM_FOR(it, n * J) {
+        const int i = it / J, j = it - i * J;
+        const int s = sh.hdr.order[i];
+        const TrkMeta& t = sh.trk[s];
+        const int last = (t.hist_start + t.hist_len - 1) % PAM_HIST;     // hist fields are stable here
+        const double* X = g.hist + ((int64_t)(s * PAM_HIST + last) * J + j) * 3;
+        const double x = X[0], y = X[1], z = X[2];
+        for (int cam = 0; cam < V; ++cam) {
+            if (counts[cam] <= 0) continue;
             const double* P = sh.P[cam];
-            double a = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[3];
-            double b = P[4] * X[0] + P[5] * X[1] + P[6] * X[2] + P[7];
-            double w = P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11];
+            double a = P[0] * x + P[1] * y + P[2] * z + P[3];
+            double b = P[4] * x + P[5] * y + P[6] * z + P[7];
+            double w = P[8] * x + P[9] * y + P[10] * z + P[11];
             double* r = sh.reproj + ((int64_t)(cam * MT + i) * J + j) * 2;
-            r[0] = b / w;   // v
-            r[1] = a / w;   // u
-        }
-        ctx.sync();
-
-        // ---- phase 2: track x detection affinity (IterativeTracker.py:139-149) ------------------
-        PAM_FOR(it, V * n * D) {
-            const int cam = it / (n * D), i = (it / D) % n, d = it % D;
-            if (d >= sh.m[cam]) continue;
-            const double* r = sh.reproj + (int64_t)(cam * MT + i) * J * 2;
-            const float* q = dets + (int64_t)(cam * D + d) * J3;
-            const double denom = c.alpha2d * (double)sh.dt[i];
-            double sum = 0.0;
-            int cnt = 0;
-            for (int j = 0; j < J; ++j) {
-                double dv = r[j * 2 + 0] - (double)q[j * 3 + 0];
-                double du = r[j * 2 + 1] - (double)q[j * 3 + 1];
-                double cj = 1.0 - sqrt(dv * dv + du * du) / denom;
-                if (cj > 0.0) { sum += cj; ++cnt; }
-            }
-            double a = (cnt > c.min_valid) ? sum / (double)cnt : 0.0;
-            a = a / exp(c.lambda_a * (double)sh.dt[i]);
-            if (a != a) a = 0.0;
-            sh.aff[(int64_t)(cam * MT + i) * D + d] = a;
-        }
-        ctx.sync();
-
-        // ---- phase 3: one assignment problem per camera (IterativeTracker.py:150-160) -----------
-        PAM_FOR(cam, V) {
-            const int mm = sh.m[cam];
-            if (mm == 0) continue;
-            const double* A = sh.aff + (int64_t)cam * MT * D;
-            int col4row[PAM_MAX_TRK];
-            lsap_solve<PAM_MAX_TRK>(n, mm, [&](int i, int d) { return -A[i * D + d]; }, col4row);
-            for (int i = 0; i < n; ++i) {
-                int d = col4row[i];
-                if (d >= 0 && A[i * D + d] > 0.0) { sh.t2d[cam][i] = (signed char)d; sh.d2t[cam][d] = (signed char)i; }
-            }
-        }
-        ctx.sync();
-
-        // ---- phase 4: add_pose in camera order (IterativeTracker.py:289-298) ---------------------
-        PAM_FOR(i, n) {
-            TrkMeta& t = sh.trk[sh.hdr.order[i]];
-            for (int cam = 0; cam < V; ++cam) {
-                if (sh.t2d[cam][i] < 0) continue;
-                int k = 0;
-                while (k < t.nviews && t.view_cid[k] != cam) ++k;
-                if (k == t.nviews) { t.nviews = k + 1; t.view_cid[k] = cam; }
-                t.view_time[k] = frame;
-                t.already = 1;
-                sh.vk[cam][i] = (signed char)k;
-            }
-        }
-        ctx.sync();
-        PAM_FOR(it, V * n * J3) {
-            const int cam = it / (n * J3), i = (it / J3) % n, e = it % J3;
-            const int d = sh.t2d[cam][i];
-            if (d < 0) continue;
-            g.view[((int64_t)(sh.hdr.order[i] * V + sh.vk[cam][i])) * J3 + e] = dets[(int64_t)(cam * D + d) * J3 + e];
+            const double iw = 1.0 / w;
+            r[0] = b * iw;   // v
+            r[1] = a * iw;   // u
         }
     }
-    if (out.assoc) {
-        PAM_FOR(it, V * D) {
-            const int cam = it / D, d = it % D;
-            int i = (d < sh.m[cam]) ? sh.d2t[cam][d] : -1;
-            out.assoc[it] = (i >= 0) ? sh.trk[sh.hdr.order[i]].track_id : -1;
+    ctx.sync();
+    PAM_MARK(0);
+
+    // ---- phase 2: track x detection affinity (IterativeTracker.py:139-149) ----------------------
+    PAM_FOR(it, V * n * D) {
+        const int cam = it / (n * D), rem = it - cam * (n * D), i = rem / D, d = rem - i * D;
+        if (d >= sh.m[cam]) continue;
+        const double* r = sh.reproj + (int64_t)(cam * MT + i) * J * 2;
+        const float* q = dets + (int64_t)(cam * D + d) * J3;
+        const double inv_denom = sh.inv_denom[i];
+        double sum = 0.0;
+        int cnt = 0;
+        for (int j = 0; j < J; ++j) {
+            double dv = r[j * 2 + 0] - (double)q[j * 3 + 0];
+            double du = r[j * 2 + 1] - (double)q[j * 3 + 1];
+            double cj = 1.0 - sqrt(dv * dv + du * du) * inv_denom;
+            if (cj > 0.0) { sum += cj; ++cnt; }
+        }
+        double a = (cnt > c.min_valid) ? sum / (double)cnt : 0.0;
+        a = a * sh.inv_decay[i];
+        if (a != a) a = 0.0;
+        sh.aff[(int64_t)(cam * MT + i) * D + d] = a;
+    }
+    ctx.sync();
+    PAM_MARK(1);
+
+    // ---- phase 3: one assignment problem per camera (IterativeTracker.py:150-160) ---------------
+    // Only pairs with affinity > 0 are ever accepted.  When the positive entries of a camera's
+    // matrix already form a matching (at most one per row and per column) every optimal assignment
+    // contains exactly those pairs, so they are taken directly; otherwise the camera is flagged
+    // and solved with the full shortest-augmenting-path algorithm below.
+    PAM_FOR(it, V * n) {
+        const int cam = it / n, i = it % n;
+        const int mm = sh.m[cam];
+        const double* A = sh.aff + (int64_t)(cam * MT) * D;
+        int cnt = 0, arg = -1;
+        for (int d = 0; d < mm; ++d)
+            if (A[i * D + d] > 0.0) { ++cnt; arg = d; }
+        if (cnt == 1) {
+            int col = 0;
+            for (int k = 0; k < n; ++k) col += (A[k * D + arg] > 0.0) ? 1 : 0;
+            if (col == 1) { sh.t2d[cam][i] = (signed char)arg; sh.d2t[cam][arg] = (signed char)i; }
+            else sh.conflict[cam] = 1;
+        } else if (cnt > 1) {
+            sh.conflict[cam] = 1;
         }
     }
+    ctx.sync();
+    {
+        int any = 0;
+        for (int cam = 0; cam < V; ++cam) any |= sh.conflict[cam];
+        if (any) {   // uniform
+            PAM_FOR(cam, V) {
+                if (!sh.conflict[cam]) continue;
+                const int mm = sh.m[cam];
+                const double* A = sh.aff + (int64_t)cam * MT * D;
+                for (int i = 0; i < n; ++i) sh.t2d[cam][i] = -1;
+                for (int d = 0; d < D; ++d) sh.d2t[cam][d] = -1;
+                int col4row[PAM_MAX_TRK];
+                lsap_solve<PAM_MAX_TRK>(n, mm, [&](int i, int d) { return -A[i * D + d]; }, col4row);
+                for (int i = 0; i < n; ++i) {
+                    int d = col4row[i];
+                    if (d >= 0 && A[i * D + d] > 0.0) { sh.t2d[cam][i] = (signed char)d; sh.d2t[cam][d] = (signed char)i; }
+                }
+            }
+            ctx.sync();
+        }
+    }
+    PAM_MARK(2);
 
-    // ---- phase 5a: gather usable views per track (IterativeTracker.py:310-325) ------------------
+    // ---- phase 4: add_pose in camera order (IterativeTracker.py:289-298), gather the usable views
+    //      of every track (:310-325); mean confidence of every detection (calculate.py:8-14) ------
     PAM_FOR(i, n) {
-        const TrkMeta& t = sh.trk[sh.hdr.order[i]];
+        TrkMeta& t = sh.trk[sh.hdr.order[i]];
+        for (int cam = 0; cam < V; ++cam) {
+            if (sh.t2d[cam][i] < 0) continue;
+            int k = 0;
+            while (k < t.nviews && t.view_cid[k] != cam) ++k;
+            if (k == t.nviews) { t.nviews = k + 1; t.view_cid[k] = cam; }
+            t.view_time[k] = frame;
+            t.already = 1;
+            sh.vk[cam][i] = (signed char)k;
+        }
         int cnt = 0;
         if (t.already)
             for (int k = 0; k < t.nviews; ++k)
                 if (frame - t.view_time[k] <= c.stale_window) sh.gv_idx[i][cnt++] = (signed char)k;
         sh.gv_n[i] = cnt;
         sh.do_update[i] = (t.already && cnt >= 2) ? 1 : 0;
-        sh.ok[i] = 0;
+    }
+    PAM_FOR(it, V * D) {
+        const int cam = it / D, d = it % D;
+        sh.um_flag[cam][d] = 0;
+        const int i = (d < sh.m[cam]) ? sh.d2t[cam][d] : -1;
+        if (out.assoc) out.assoc[it] = (i >= 0) ? sh.trk[sh.hdr.order[i]].track_id : -1;
+        if (d >= sh.m[cam]) continue;
+        const float* q = dets + (int64_t)(cam * D + d) * J3;
+        double kept[PAM_MAX_J];
+        int nk = 0;
+        for (int j = 0; j < J; ++j)
+            if (q[j * 3 + 2] >= 0.0f) kept[nk++] = (double)q[j * 3 + 2];
+        double b = np_sum(kept, nk) / (double)nk;   // 0/0 -> NaN like np.mean([])
+        sh.believe[cam][d] = b;
+        sh.um_flag[cam][d] = (i < 0 && b > c.conf_thr) ? 1 : 0;
     }
     ctx.sync();
+    PAM_MARK(3);
 
-    // ---- phase 5b: per (track, joint): part-aware view filter + DLT (IterativeTracker.py:337-369)
+    // ---- phase 5: per (track, joint): part-aware view filter + DLT (IterativeTracker.py:337-369);
+    //      persist the matched detections as the tracks' newest views; unmatched lists ---------
     PAM_FOR(it, n * J) {
-        const int i = it / J, j = it % J;
+        const int i = it / J, j = it - i * J;
         if (!sh.do_update[i]) continue;
         const int s = sh.hdr.order[i];
         const TrkMeta& t = sh.trk[s];
@@ -450,139 +540,152 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         const int Vt = sh.gv_n[i];
         for (int a = 0; a < Vt; ++a) {
             const int k = sh.gv_idx[i][a];
-            cid[a] = t.view_cid[k];
+            const int cam = t.view_cid[k];
+            cid[a] = cam;
             T[a] = frame - t.view_time[k];
-            const float* q = g.view + ((int64_t)(s * V + k) * J + j) * 3;
+            // a view matched this frame is read straight from the staged detections
+            const float* q = (T[a] == 0) ? dets + ((int64_t)(cam * D + sh.t2d[cam][i]) * J + j) * 3
+                                         : g.view + ((int64_t)(s * V + k) * J + j) * 3;
             v[a] = (double)q[0];
             u[a] = (double)q[1];
         }
         double X[3];
-        int nv = joint_update(c, sh, Vt, cid, T, u, v, next, X);
+        const int nv = joint_update(c, sh, Vt, cid, T, u, v, next, X);
         sh.nvj[i][j] = (unsigned char)nv;
+        if (nv < 2) ctx.atomic_inc(&sh.fail[i]);
         double* r = sh.raw + (int64_t)(i * J + j) * 3;
         r[0] = X[0]; r[1] = X[1]; r[2] = X[2];
     }
-    ctx.sync();
-
-    // ---- phase 5c: success test, ring slot for the new pose ------------------------------------
-    PAM_FOR(i, n) {
-        if (!sh.do_update[i]) continue;
-        TrkMeta& t = sh.trk[sh.hdr.order[i]];
-        int fail = 0;
-        for (int j = 0; j < J; ++j) fail += (sh.nvj[i][j] < 2) ? 1 : 0;
-        if ((double)fail > c.fail_limit) continue;
-        if (t.hist_len >= PAM_HIST) { sh.hdr.status = SEQ_ERR_HIST_OVERFLOW; continue; }
-        sh.ok[i] = 1;
-        const int pos = (t.hist_start + t.hist_len) % PAM_HIST;
-        sh.newpos[i] = pos;
-        t.hist_time[pos] = frame;
+    {   // J3 consecutive floats per matched (camera, track) pair; lanes stride over the elements
+        const int lanes = (ctx.nthreads() >= 32) ? 32 : ctx.nthreads();
+        const int grp = ctx.tid() / lanes, ngrp = ctx.nthreads() / lanes, lane = ctx.tid() - grp * lanes;
+        for (int p = grp; p < V * n; p += ngrp) {
+            const int cam = p / n, i = p - cam * n;
+            const int d = sh.t2d[cam][i];
+            if (d < 0) continue;
+            float* dst = g.view + ((int64_t)(sh.hdr.order[i] * V + sh.vk[cam][i])) * J3;
+            const float* src = dets + (int64_t)(cam * D + d) * J3;
+            for (int e = lane; e < J3; e += lanes) dst[e] = src[e];
+        }
+    }
+    PAM_FOR(cam, V) {
+        int k = 0;
+        for (int d = 0; d < sh.m[cam]; ++d)
+            if (sh.um_flag[cam][d]) sh.um[cam][k++] = (signed char)d;
+        sh.um_n[cam] = k;
     }
     ctx.sync();
+    PAM_MARK(4);
 
-    // ---- phase 5d: temporal Gaussian, last sample (IterativeTracker.py:371-383) -----------------
+    // ---- phase 6: per (track, joint) of every successfully updated track: temporal Gaussian, last
+    //      sample (IterativeTracker.py:371-383), history append, velocity = float32 mean of the
+    //      last <= 5 differences (:385-395), output row (ivclabpose.py:265-287) ------------------
     PAM_FOR(it, n * J) {
-        const int i = it / J, j = it % J;
-        if (!sh.ok[i]) continue;
+        const int i = it / J, j = it - i * J;
+        if (!track_ok(c, sh, i)) continue;
         const int s = sh.hdr.order[i];
-        const TrkMeta& t = sh.trk[s];
+        TrkMeta& t = sh.trk[s];
         const int which = (c.arm_mask >> j) & 1u;
         const int rad = c.rad[which];
         const double* w = c.gw[which];
         const int L = t.hist_len, N = L + 1;       // series = history + current raw pose
+        const int start = t.hist_start;
+        const int pos = (start + L) % PAM_HIST;
         const double* raw = sh.raw + (int64_t)(i * J + j) * 3;
-        double* dst = g.hist + ((int64_t)(s * PAM_HIST + sh.newpos[i]) * J + j) * 3;
+        const double* hb = g.hist + ((int64_t)(s * PAM_HIST) * J + j) * 3;   // + ring * J3
         double o0 = raw[0] * w[0], o1 = raw[1] * w[0], o2 = raw[2] * w[0];
         for (int k = rad; k >= 1; --k) {
             const int il = reflect_index(L - k, N), ir = reflect_index(L + k, N);
-            const double* xl = (il == L) ? raw : g.hist + ((int64_t)(s * PAM_HIST + (t.hist_start + il) % PAM_HIST) * J + j) * 3;
-            const double* xr = (ir == L) ? raw : g.hist + ((int64_t)(s * PAM_HIST + (t.hist_start + ir) % PAM_HIST) * J + j) * 3;
+            const double* xl = (il == L) ? raw : hb + (int64_t)((start + il) % PAM_HIST) * J3;
+            const double* xr = (ir == L) ? raw : hb + (int64_t)((start + ir) % PAM_HIST) * J3;
             o0 += (xl[0] + xr[0]) * w[k];
             o1 += (xl[1] + xr[1]) * w[k];
             o2 += (xl[2] + xr[2]) * w[k];
         }
+        // window after the append and the at-most-one-entry trim (IterativeTracker.py:330-332)
+        int len2 = L + 1, start2 = start;
+        if (frame - t.hist_time[start] > c.max_age) { start2 = (start + 1) % PAM_HIST; len2 -= 1; }
+        if (len2 >= 2) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            float h0 = (float)o0, h1 = (float)o1, h2 = (float)o2;    // newest entry = this frame's pose
+            int cnt = 0;
+            for (int idx = len2 - 1; idx >= 1 && cnt < 5; --idx, ++cnt) {
+                const double* lo = hb + (int64_t)((start2 + idx - 1) % PAM_HIST) * J3;
+                const float l0 = (float)lo[0], l1 = (float)lo[1], l2 = (float)lo[2];
+                a0 += h0 - l0; a1 += h1 - l1; a2 += h2 - l2;
+                h0 = l0; h1 = l1; h2 = l2;
+            }
+            float* vel = g.vel + (int64_t)(s * J + j) * 3;
+            const float fc = (float)cnt;
+            vel[0] = a0 / fc; vel[1] = a1 / fc; vel[2] = a2 / fc;
+        }
+        double* dst = g.hist + ((int64_t)(s * PAM_HIST + pos) * J + j) * 3;
         dst[0] = o0; dst[1] = o1; dst[2] = o2;
         g.nv[s * J + j] = sh.nvj[i][j];
-    }
-    ctx.sync();
-
-    // ---- phase 5e: history trim + life-cycle (IterativeTracker.py:253-274, 329-333) -------------
-    PAM_FOR(i, n) {
-        TrkMeta& t = sh.trk[sh.hdr.order[i]];
-        if (sh.ok[i]) {
-            t.hist_len += 1;
-            if (frame - t.hist_time[t.hist_start] > c.max_age) {
-                t.hist_start = (t.hist_start + 1) % PAM_HIST;
-                t.hist_len -= 1;
-            }
-            t.hits += 1;
-            t.tsu = 0;
-            if (t.state == ST_TENTATIVE && t.hits >= c.n_init) t.state = ST_CONFIRMED;
-        } else {
-            if (t.state == ST_TENTATIVE && !t.already) t.state = ST_DELETED;
-            else if (t.tsu >= c.max_age) t.state = ST_DELETED;
-        }
-    }
-    ctx.sync();
-
-    // ---- phase 5f: velocity = float32 mean of the last <= 5 differences (IterativeTracker.py:385-395)
-    PAM_FOR(it, n * J) {
-        const int i = it / J, j = it % J;
-        if (!sh.ok[i]) continue;
-        const int s = sh.hdr.order[i];
-        const TrkMeta& t = sh.trk[s];
-        if (t.hist_len < 2) continue;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-        int cnt = 0;
-        for (int idx = t.hist_len - 1; idx >= 1 && cnt < 5; --idx, ++cnt) {
-            const double* hi = g.hist + ((int64_t)(s * PAM_HIST + (t.hist_start + idx) % PAM_HIST) * J + j) * 3;
-            const double* lo = g.hist + ((int64_t)(s * PAM_HIST + (t.hist_start + idx - 1) % PAM_HIST) * J + j) * 3;
-            a0 += (float)hi[0] - (float)lo[0];
-            a1 += (float)hi[1] - (float)lo[1];
-            a2 += (float)hi[2] - (float)lo[2];
-        }
-        float* vel = g.vel + (int64_t)(s * J + j) * 3;
-        const float fc = (float)cnt;
-        vel[0] = a0 / fc; vel[1] = a1 / fc; vel[2] = a2 / fc;
-    }
-
-    // ---- phase 6: new-track initialisation (IterativeTracker.py:52-113) -------------------------
-    // 6a: mean confidence of every detection; unmatched + confident ones take part
-    PAM_FOR(it, V * D) {
-        const int cam = it / D, d = it % D;
-        sh.um_flag[cam][d] = 0;
-        if (d >= sh.m[cam]) continue;
-        const float* q = dets + (int64_t)(cam * D + d) * J3;
-        double kept[PAM_MAX_J];
-        int nk = 0;
-        for (int j = 0; j < J; ++j)
-            if (q[j * 3 + 2] >= 0.0f) kept[nk++] = (double)q[j * 3 + 2];
-        double b = np_sum(kept, nk) / (double)nk;   // 0/0 -> NaN like np.mean([])
-        sh.believe[cam][d] = b;
-        sh.um_flag[cam][d] = (sh.d2t[cam][d] < 0 && b > c.conf_thr) ? 1 : 0;
-    }
-    ctx.sync();
-    if (ctx.tid() == 0) {
-        int cams_with = 0;
-        for (int cam = 0; cam < V; ++cam) {
+        if (j == 0) t.hist_time[pos] = frame;     // no other thread reads this entry in this phase
+        if (track_reported(c, sh, i)) {
             int k = 0;
-            for (int d = 0; d < sh.m[cam]; ++d)
-                if (sh.um_flag[cam][d]) sh.um[cam][k++] = (signed char)d;
-            sh.um_n[cam] = k;
-            cams_with += (k > 0);
+            for (int i2 = 0; i2 < i; ++i2) k += track_reported(c, sh, i2) ? 1 : 0;
+            if (out.joints) {
+                float* oj = out.joints + (int64_t)(k * J + j) * 3;
+                oj[0] = (float)o0; oj[1] = (float)o1; oj[2] = (float)o2;
+            }
+            if (out.nviews) out.nviews[k * J + j] = sh.nvj[i][j];
         }
+    }
+    ctx.sync();
+    PAM_MARK(5);
+
+    // ---- phase 7: life-cycle (IterativeTracker.py:253-274), reported ids, reap (:178), and the
+    //      decision whether new-track initialisation has anything to do ---------------------------
+    if (ctx.tid() == 0) {
+        int k = 0, wr = 0;
+        for (int i = 0; i < n; ++i) {
+            const int s = sh.hdr.order[i];
+            TrkMeta& t = sh.trk[s];
+            if (sh.do_update[i] && !((double)sh.fail[i] > c.fail_limit) && t.hist_len >= PAM_HIST)
+                sh.hdr.status = SEQ_ERR_HIST_OVERFLOW;
+            if (track_ok(c, sh, i)) {
+                t.hist_len += 1;
+                if (frame - t.hist_time[t.hist_start] > c.max_age) {
+                    t.hist_start = (t.hist_start + 1) % PAM_HIST;
+                    t.hist_len -= 1;
+                }
+                t.hits += 1;
+                t.tsu = 0;
+                if (t.state == ST_TENTATIVE && t.hits >= c.n_init) t.state = ST_CONFIRMED;
+                if (t.state == ST_CONFIRMED) {
+                    if (out.ids) out.ids[k] = t.track_id;
+                    ++k;
+                }
+            } else {
+                if (t.state == ST_TENTATIVE && !t.already) t.state = ST_DELETED;
+                else if (t.tsu >= c.max_age) t.state = ST_DELETED;
+            }
+            if (t.state == ST_DELETED) sh.hdr.used_mask &= ~(1u << s);
+            else sh.hdr.order[wr++] = s;
+        }
+        sh.hdr.ntracks = wr;
+        sh.hdr.frames_done += 1;
+        if (out.count) *out.count = k;
+        int cams_with = 0;
+        for (int cam = 0; cam < V; ++cam) cams_with += (sh.um_n[cam] > 0);
         // a hypothesis needs views from two cameras to become a track (hypothesis.size() > 1)
         sh.do_init = (V >= 2 && cams_with >= 2) ? 1 : 0;
         sh.hyp_n = 0;
         if (sh.do_init) {
-            for (int k = 0; k < sh.um_n[0]; ++k) {
-                sh.hyp_nviews[k] = 1; sh.hyp_cam[k][0] = 0; sh.hyp_det[k][0] = sh.um[0][k];
+            for (int q = 0; q < sh.um_n[0]; ++q) {
+                sh.hyp_nviews[q] = 1; sh.hyp_cam[q][0] = 0; sh.hyp_det[q][0] = sh.um[0][q];
             }
             sh.hyp_n = sh.um_n[0];
         }
     }
     ctx.sync();
+    PAM_MARK(6);
+
+    // ---- phase 8: new-track initialisation (IterativeTracker.py:52-113); rare in steady state ---
     if (sh.do_init) {
-        // 6c: grow hypotheses camera by camera
+        // grow hypotheses camera by camera
         for (int cam = 1; cam < V; ++cam) {
             const int nh = sh.hyp_n, nd = sh.um_n[cam];
             if (nd == 0) continue;           // uniform
@@ -621,7 +724,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             }
             ctx.sync();
         }
-        // 6d: first triangulation of every multi-view hypothesis (hypothesis.py:23-44)
+        // first triangulation of every multi-view hypothesis (hypothesis.py:23-44)
         const int nh = sh.hyp_n;
         PAM_FOR(h, nh) sh.hyp_fail[h] = (sh.hyp_nviews[h] < 2) ? 1 : 0;
         ctx.sync();
@@ -643,7 +746,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             r[0] = X[0]; r[1] = X[1]; r[2] = X[2];
         }
         ctx.sync();
-        // 6e: spawn tracks in hypothesis order (IterativeTracker.py:102-113)
+        // spawn tracks in hypothesis order (IterativeTracker.py:102-113)
         if (ctx.tid() == 0) {
             for (int h = 0; h < nh; ++h) {
                 sh.hyp_slot[h] = -1;
@@ -674,41 +777,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             if (e < J) g.nv[s * J + e] = sh.hyp_nvj[h][e];
         }
     }
-    ctx.sync();
-
-    // ---- phase 7: output contract + reap (ivclabpose.py:265-287, IterativeTracker.py:178) -------
-    if (ctx.tid() == 0) {
-        int k = 0, w = 0;
-        for (int i = 0; i < sh.hdr.ntracks; ++i) {
-            const int s = sh.hdr.order[i];
-            const TrkMeta& t = sh.trk[s];
-            if (t.state == ST_CONFIRMED && t.tsu == 0) {
-                sh.out_slot[k] = (signed char)s;
-                if (out.ids) out.ids[k] = t.track_id;
-                ++k;
-            }
-            if (t.state == ST_DELETED) sh.hdr.used_mask &= ~(1u << s);
-            else sh.hdr.order[w++] = s;
-        }
-        sh.hdr.ntracks = w;
-        sh.out_n = k;
-        sh.hdr.frames_done += 1;
-        if (out.count) *out.count = k;
-    }
-    ctx.sync();
-    if (out.joints) {
-        PAM_FOR(it, sh.out_n * J3) {
-            const int k = it / J3, e = it % J3;
-            const int s = sh.out_slot[k];
-            const TrkMeta& t = sh.trk[s];
-            const int last = (t.hist_start + t.hist_len - 1) % PAM_HIST;
-            out.joints[it] = (float)g.hist[(int64_t)(s * PAM_HIST + last) * J3 + e];
-        }
-    }
-    if (out.nviews) {
-        PAM_FOR(it, sh.out_n * J) out.nviews[it] = g.nv[sh.out_slot[it / J] * J + it % J];
-    }
-    ctx.sync();
+    PAM_MARK(7);
 }
 
 }  // namespace pam

@@ -60,3 +60,29 @@ extern "C" int hostemu_state_layout(const pam_config* cfg, pam_state_layout* L) 
     fill_layout(c, *L);
     return PAM_OK;
 }
+
+// DLT extractor check: n joints, V views each; mode 0 = product policy (Gram when all weights are 1),
+// 1 = force Givens + inverse iteration/Jacobi, 2 = force Givens + Jacobi only.
+extern "C" int hostemu_dlt(int n, int V, const double* P, const double* uv, const double* w, const uint8_t* keep,
+                           int mode, double* X, int* path) {
+    for (int i = 0; i < n; ++i) {
+        bool fresh = true;
+        for (int a = 0; a < V; ++a) if (keep[i * V + a] && w[i * V + a] != 1.0) fresh = false;
+        DltAccum acc;
+        int how = -1;
+        if (mode == 0 && fresh) {
+            acc.reset(true);
+            for (int a = 0; a < V; ++a) if (keep[i * V + a]) acc.add_view(P + a * 12, uv[(i * V + a) * 2], uv[(i * V + a) * 2 + 1], 1.0);
+            acc.solve(X + i * 3, &how);
+            if (how >= 0) how += 10;
+        }
+        if (how < 0) {
+            acc.reset(false);
+            for (int a = 0; a < V; ++a) if (keep[i * V + a]) acc.add_view(P + a * 12, uv[(i * V + a) * 2], uv[(i * V + a) * 2 + 1], w[i * V + a]);
+            if (mode == 2) { double x[4]; acc.jacobi(x); X[i*3] = x[0]/x[3]; X[i*3+1] = x[1]/x[3]; X[i*3+2] = x[2]/x[3]; how = 1; }
+            else acc.solve(X + i * 3, &how);
+        }
+        path[i] = how;
+    }
+    return 0;
+}
