@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- synthetic multi-view frames/s (triangulated + associated) of the part-aware tracker.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], batched as configs[4]): Shelf-shaped synthetic streams -- 5
+cameras, 4 people, 14 joints, 3200 frames per sequence -- S independent sequences per GPU (weak
+scaling: every rank tracks its own S sequences; sequences never span GPUs).  One "step" = one pass
+of the tracker over all S x T frames of the rank, starting from empty trackers.
+
+Printed JSON keys follow the driver contract:
+  value      whole-job frames/s with detections already resident in HBM (restart + kernel), CUDA
+             events on the launching stream, max over ranks
+  e2e        the same through the reference-facing C-ABI call pam_track_sequences_host with pinned
+             HOST buffers: H2D of the detections, kernel, D2H of ids/joints, inside the timed region
+  roofline   the tracker kernel against the measured HBM copy peak (MEASURED_PEAKS.json); the
+             kernel is FP64-latency/issue bound, so the fraction is small by construction
+             (DESIGN.md section "Roofline")
+  cpu_baseline  the numpy oracle (oracle/generic.py, a bit-identical restatement of the reference's
+             own per-frame path) timed on one host core over a bounded prefix of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SHAPE = "shelf"
+METRIC = "synthetic multi-view frames/sec (triangulated+associated)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sequences", type=int, default=592, help="independent sequences per GPU (148 SMs x 4 CTAs)")
+    ap.add_argument("--frames", type=int, default=None, help="frames per sequence (default: the shape's 3200)")
+    ap.add_argument("--shape", default=SHAPE)
+    ap.add_argument("--cpu-frames", type=int, default=2000, help="frames of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# data
+# ----------------------------------------------------------------------------------------------
+def generate(shape, seq_ids, T, dets_out, counts_out, workers=None):
+    from concurrent.futures import ThreadPoolExecutor
+    import pam_b200  # noqa: F401
+    from pam_b200 import synth
+    rig = synth.make_rig(shape)
+
+    def one(k):
+        st = synth.make_stream(shape, seq_ids[k], T, rig=rig)
+        dets_out[k] = st.dets
+        counts_out[k] = st.counts
+
+    with ThreadPoolExecutor(workers or min(32, os.cpu_count() or 8)) as ex:
+        list(ex.map(one, range(len(seq_ids))))
+    return rig
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_evt.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                p = [x.strip() for x in o.strip().split(",")]
+                if len(p) >= 7:
+                    self.rows.append(p)
+            except Exception:
+                pass
+            self.stop_evt.wait(0.15)
+
+    def summary(self):
+        self.stop_evt.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference's per-frame path (oracle port) on the host cores
+# ----------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    shape, seq_id, frames, warm = args
+    import pam_b200  # noqa: F401
+    from pam_b200 import synth
+    from oracle import generic
+    st = synth.make_stream(shape, seq_id, frames + warm)
+    cams = generic.build_cameras(st.rig["P"], st.rig["K"], st.rig["RT"])
+    trk = generic.Tracker(synth.tracker_params(shape), st.shape.arm_joints, 10)
+    V = st.shape.V
+    inputs = [(st.frame_boxes(t), st.frame_detections(t)) for t in range(st.T)]
+    for t in range(warm):        # first frames discarded like src/testmodel.py:86
+        trk.tracking(t, cams, [None] * V, inputs[t][0], inputs[t][1], "SVD")
+    t0 = time.perf_counter()
+    for t in range(warm, st.T):  # timer around tracking() only, like src/evalmodel.py:79-82
+        trk.tracking(t, cams, [None] * V, inputs[t][0], inputs[t][1], "SVD")
+    return time.perf_counter() - t0
+
+
+def cpu_sample(shape, frames, procs, seq0=900000, warm=10):
+    """frames/s of the oracle over `procs` processes, one sequence prefix each."""
+    if procs == 1:
+        el = _cpu_worker((shape, seq0, frames, warm))
+        return frames / el, el
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        t0 = time.perf_counter()
+        els = pool.map(_cpu_worker, [(shape, seq0 + k, frames, warm) for k in range(procs)])
+        wall = time.perf_counter() - t0
+    # aggregate rate = sum of the per-process rates (each process times only tracking())
+    return sum(frames / e for e in els), wall
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from pam_b200 import synth
+    sh = synth.SHAPES[a.shape]
+    cores = os.cpu_count() or 1
+    frames = 250                     # per process per step: ~2 s of CPU work
+    rates = []
+    for it in range(a.warmup + a.steps):
+        r, _ = cpu_sample(a.shape, frames, cores, seq0=900000 + 1000 * it)
+        if it >= a.warmup:
+            rates.append(r)
+    val = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * frames * cores / val, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{a.shape}: {sh.V} cameras x {sh.P} people x {sh.J} joints, {cores} sequences x "
+                               f"{frames} frames per step (bounded sample of the {sh.T}-frame streams)"},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{cores} processes x {frames} frames, numpy oracle (bit-identical restatement of "
+                                   "the reference's IterativeTracker.tracking), timer around tracking() only"},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import pam_b200  # noqa: F401
+    from pam_b200 import camera, dist as pdist, synth, tracker
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    rank, local_rank, world = pdist.init()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    sh = synth.SHAPES[a.shape]
+    S, T = a.sequences, (a.frames or sh.T)
+    V, J, D = sh.V, sh.J, sh.P
+    MT = 8 if sh.P <= 6 else 12
+
+    # ---- synthetic input, generated straight into pinned host memory ---------------------------
+    h_dets = torch.empty((S, T, V, D, J, 3), dtype=torch.float32, pin_memory=True)
+    h_counts = torch.empty((S, T, V), dtype=torch.int32, pin_memory=True)
+    seq_ids = [rank * S + s for s in range(S)]          # distinct seeds on every rank
+    t0 = time.time()
+    rig = generate(a.shape, seq_ids, T, h_dets.numpy(), h_counts.numpy())
+    gen_s = time.time() - t0
+    cams = camera.GetCameraParameters(rig)
+    trk = tracker.SequenceTracker(cams, synth.tracker_params(a.shape), S, max_detections=D, max_tracks=MT,
+                                  arm_joints=sh.arm_joints, device=local_rank)
+    d_dets = h_dets.to(dev, non_blocking=True)
+    d_counts = h_counts.to(dev, non_blocking=True)
+    out = trk.alloc_outputs(T, nviews=False, assoc=False)
+    counters = torch.zeros(4, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(timed_events=None):
+        trk.restart()                                    # empty trackers: every step does the same work
+        if timed_events is not None:
+            timed_events[0].record(stream)
+        trk.run(d_dets, d_counts, out=out, frame0=0)
+        if timed_events is not None:
+            timed_events[1].record(stream)
+        # run counters (reports, frames); summed over ranks -- the only collective of the path
+        counters[0] = out["count"].sum()
+        counters[1] = S * T
+        pdist.reduce_counters(counters)
+
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    trk.check()
+    launches0 = trk.launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pdist.barrier()
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for k in range(a.steps):
+        step(kev[k])
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    pdist.barrier()
+    elapsed_ms = pdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    clocks = sampler.summary()
+    launches = trk.launches - launches0
+    trk.check()
+    kernel_ms = float(np.mean([x.elapsed_time(y) for x, y in kev]))
+    reports = int(out["count"].sum().item())
+    total_frames = world * S * T
+    value = total_frames * a.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        ho = dict(count=torch.empty((S, T), dtype=torch.int32, pin_memory=True).numpy(),
+                  ids=torch.empty((S, T, MT), dtype=torch.int32, pin_memory=True).numpy(),
+                  joints=torch.empty((S, T, MT, J, 3), dtype=torch.float32, pin_memory=True).numpy(),
+                  nviews=None, assoc=None)
+        hd, hc = h_dets.numpy(), h_counts.numpy()
+        for _ in range(max(1, min(a.warmup, 2))):
+            trk.run_host(hd, hc, fresh=True, nviews=False, out=ho)
+        pdist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            trk.run_host(hd, hc, fresh=True, nviews=False, out=ho)
+        torch.cuda.synchronize(dev)
+        el = pdist.max_over_ranks(time.perf_counter() - t0, dev)
+        assert int(ho["count"].sum()) == reports, "host path and device path disagree"
+        e2e = {"value": total_frames * a.steps / el, "unit": "frames/s",
+               "h2d_bytes_per_step": int(h_dets.numel() * 4 + h_counts.numel() * 4) * world,
+               "d2h_bytes_per_step": int(ho["count"].nbytes + ho["ids"].nbytes + ho["joints"].nbytes) * world,
+               "ms_per_step": 1e3 * el / a.steps, "timer": "host wall clock around the synchronous C-ABI call"}
+
+    if rank != 0:
+        return
+
+    # ---- roofline of the tracker kernel ----------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    n_out = reports / float(S * T)
+    b_frame = 4.0 * (3 * V * D * J + 3 * n_out * J + n_out)
+    achieved = b_frame * S * T / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "kernel": "k_track_sequences", "kernel_ms": kernel_ms, "bytes_per_frame": b_frame,
+                "note": "frame-serial FP64 state machine: latency/FP64-issue bound, not HBM bound"}
+
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        rate, el = cpu_sample(a.shape, a.cpu_frames, 1)
+        cpu = {"value": rate, "unit": "frames/s", "cores": 1, "kind": "port",
+               "sample": f"first {a.cpu_frames} frames of one {a.shape} sequence after 10 warm-up frames "
+                         f"({el:.1f} s), numpy oracle = bit-identical restatement of the reference path"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{a.shape}: {V} cameras x {sh.P} people x {J} joints x {T} frames, {S} independent "
+                               f"sequences per GPU", "sequences_per_gpu": S, "frames": T, "max_tracks": MT,
+                   "l2": f"inputs larger than L2 ({d_dets.numel() * 4 / 1e9:.2f} GB of detections per GPU per step)",
+                   "gen_seconds": round(gen_s, 1), "reports_per_step": int(counters[0].item()),
+                   "threads_per_cta": int(os.environ.get("PAM_TRACK_THREADS", "0")) or "auto"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -31,7 +31,7 @@ extern "C" {
 #define PAM_ABI_VERSION 1
 
 /* compile-time capacity limits of the stateful tracker (pam_core.h) */
-#define PAM_LIMIT_CAMERAS 8
+#define PAM_LIMIT_CAMERAS 8        /* stateful tracker; stateless ops: 32 */
 #define PAM_LIMIT_TRACKS 16
 #define PAM_LIMIT_DETECTIONS 16
 #define PAM_LIMIT_JOINTS 32
@@ -136,6 +136,61 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
 
 /* Copy the internal state of the _host path (S sequences) to a host buffer of S*seq_bytes. */
 int pam_track_state_to_host(pam_handle* h, int32_t S, void* h_state);
+
+/* ---- stateless batched ops (device pointers, asynchronous on `stream`) ------------------------
+ * Camera constants come from pam_set_cameras; J = cfg.num_joints; up to 32 cameras. */
+
+/* Camera.projectPoints_parallel (ivclabpose.py:91-98) for all cameras at once:
+ * d_points3d [n_points][3] f64 -> d_out_vu [V][n_points][2] f64 as (v, u). */
+int pam_project_points(pam_handle* h, const double* d_points3d, int32_t n_points, double* d_out_vu, void* stream);
+
+/* Association affinity of tracking() (tracking/IterativeTracker.py:137-149) for all cameras:
+ * d_tracks3d [n][J][3] f64, d_dt [n] i32 (frame - last pose time), d_dets [V][max_dets][J][3] f64
+ * (v,u,conf), d_counts [V] i32 -> d_aff [V][n][max_dets] f64 (0 beyond counts). */
+int pam_assoc_affinity(pam_handle* h, const double* d_tracks3d, const int32_t* d_dt, const double* d_dets,
+                       const int32_t* d_counts, int32_t n_tracks, int32_t max_dets, double* d_aff, void* stream);
+
+/* scipy.optimize.linear_sum_assignment (call sites tracking/IterativeTracker.py:79,150), batched:
+ * d_cost [batch][n_rows][n_cols] f64 -> d_col4row [batch][n_rows] i32 (-1 = unassigned);
+ * n_rows, n_cols <= 64. */
+int pam_assign(pam_handle* h, const double* d_cost, int32_t batch, int32_t n_rows, int32_t n_cols, int32_t maximize,
+               int32_t* d_col4row, void* stream);
+
+/* epipolar_affinity_parallel (utils/matching.py:115-151): d_pose [M][J][3] f64 (v,u,conf),
+ * d_cam [M] i32 camera index per pose -> d_dist [M][M][J] f64, d_mean [M][M] f64. */
+int pam_epipolar_pairs(pam_handle* h, const double* d_pose, const int32_t* d_cam, int32_t M, double* d_dist,
+                       double* d_mean, void* stream);
+
+/* epipolar_affinity (utils/matching.py:93-113), float32 stores: d_aff [M][M] f32 (25 between poses of
+ * one camera, 0 on the diagonal), d_dist_or_null [M][M][J] f32. */
+int pam_epipolar_allpairs(pam_handle* h, const double* d_pose, const int32_t* d_cam, int32_t M, float* d_aff,
+                          float* d_dist_or_null, void* stream);
+
+/* epipolar_distance (utils/matching.py:50-91) for `batch` pose pairs: d_pose1/2 [batch][J][3] f64,
+ * d_cam1/2 [batch] i32 -> d_out [batch][J][2] f64 = [d(x1, F x2), d(x2, F^T x1)]. */
+int pam_epipolar_distance(pam_handle* h, const double* d_pose1, const double* d_pose2, const int32_t* d_cam1,
+                          const int32_t* d_cam2, int32_t batch, double* d_out, void* stream);
+
+/* Greedy_matching (utils/matching.py:243-295) for `batch` joints over n_views views:
+ * mode 0 'update': d_affinity_f64 [batch][n][n], d_uv [batch][n][2] (u,v), d_next [batch][3];
+ * mode 1 'init':   d_affinity_f32 [batch][n][n];   d_cam [n] i32 -> d_keep [batch][n] u8. */
+int pam_view_filter(pam_handle* h, int32_t mode, const double* d_affinity_f64, const float* d_affinity_f32,
+                    const double* d_uv, const int32_t* d_cam, const double* d_next, int32_t batch, int32_t n_views,
+                    uint8_t* d_keep, void* stream);
+
+/* SVD_pose_kernel_jf / _parallel / SVD_pose_kernel (utils/construction.py:64-131): d_pose
+ * [batch][n_views][J][3] f64, d_cam [batch][n_views] i32, d_weight [batch][n_views] f64
+ * (exp(-lambda_t T)), d_keep_or_null [batch][J][n_views] u8, d_next_or_null [batch][J][3] f64 (value of
+ * joints with < 2 views; NaN if null) -> d_out [batch][J][3] f64. */
+int pam_triangulate(pam_handle* h, const double* d_pose, const int32_t* d_cam, const double* d_weight,
+                    const uint8_t* d_keep_or_null, const double* d_next_or_null, int32_t batch, int32_t n_views,
+                    double* d_out, void* stream);
+
+/* back_project_ray (utils/matching.py:10-17) + line2point_distance_3D (utils/calculate.py:26-32):
+ * d_uv [n][2] f64 (u,v) -> d_dirs_or_null [n][3] unit rays, d_dist_or_null [n] distance of
+ * d_points3d_or_null [n][3] to the rays. */
+int pam_ray_distance(pam_handle* h, int32_t camera, const double* d_uv, const double* d_points3d_or_null, int32_t n,
+                     double* d_dist_or_null, double* d_dirs_or_null, void* stream);
 
 /* number of kernel launches issued through this handle so far (bench.py "gpu_launches") */
 int64_t pam_launch_count(const pam_handle* h);

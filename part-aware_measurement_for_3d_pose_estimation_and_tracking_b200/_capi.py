@@ -71,6 +71,15 @@ _PROTOTYPES = [
     ("pam_track_sequences_host", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     ("pam_track_state_to_host", C.c_int, [_P, C.c_int32, _P]),
     ("pam_launch_count", C.c_int64, [_P]),
+    ("pam_project_points", C.c_int, [_P, _P, C.c_int32, _P, _P]),
+    ("pam_assoc_affinity", C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
+    ("pam_assign", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    ("pam_epipolar_pairs", C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P]),
+    ("pam_epipolar_allpairs", C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P]),
+    ("pam_epipolar_distance", C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P, _P]),
+    ("pam_view_filter", C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
+    ("pam_triangulate", C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
+    ("pam_ray_distance", C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, _P, _P, _P]),
 ]
 
 

@@ -373,7 +373,7 @@ PAM_HD_NOINLINE int lsap_solve(int nr0, int nc0, CostFn cost, int* col4row_out) 
     const int nr = transpose ? nc0 : nr0, nc = transpose ? nr0 : nc0;
     double u[MAXN], v[MAXN], sp[MAXN];
     int path[MAXN], col4row[MAXN], row4col[MAXN], remaining[MAXN];
-    uint32_t SR, SC;
+    uint64_t SR, SC;
     for (int i = 0; i < nr; ++i) { u[i] = 0.0; col4row[i] = -1; }
     for (int j = 0; j < nc; ++j) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
     const double INF = HUGE_VAL;
@@ -382,12 +382,12 @@ PAM_HD_NOINLINE int lsap_solve(int nr0, int nc0, CostFn cost, int* col4row_out) 
         int i = cur;
         int num_remaining = nc;
         for (int it = 0; it < nc; ++it) { remaining[it] = nc - it - 1; sp[it] = INF; }
-        SR = 0u; SC = 0u;
+        SR = 0ull; SC = 0ull;
         int sink = -1;
         while (sink == -1) {
             int index = -1;
             double lowest = INF;
-            SR |= (1u << i);
+            SR |= (1ull << i);
             for (int it = 0; it < num_remaining; ++it) {
                 int j = remaining[it];
                 double cij = transpose ? cost(j, i) : cost(i, j);
@@ -399,14 +399,14 @@ PAM_HD_NOINLINE int lsap_solve(int nr0, int nc0, CostFn cost, int* col4row_out) 
             if (minVal == INF) return -1;
             int j = remaining[index];
             if (row4col[j] == -1) sink = j; else i = row4col[j];
-            SC |= (1u << j);
+            SC |= (1ull << j);
             remaining[index] = remaining[--num_remaining];
         }
         u[cur] += minVal;
         for (int k = 0; k < nr; ++k)
-            if (((SR >> k) & 1u) && k != cur) u[k] += minVal - sp[col4row[k]];
+            if (((SR >> k) & 1ull) && k != cur) u[k] += minVal - sp[col4row[k]];
         for (int j = 0; j < nc; ++j)
-            if ((SC >> j) & 1u) v[j] -= minVal - sp[j];
+            if ((SC >> j) & 1ull) v[j] -= minVal - sp[j];
         int j = sink;
         while (true) {
             int k = path[j];

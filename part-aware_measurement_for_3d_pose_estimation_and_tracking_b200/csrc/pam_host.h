@@ -7,9 +7,13 @@
 
 namespace pam {
 
+// true when the configuration fits the stateful tracker's compile-time capacities (<= 8 cameras);
+// rigs with up to 32 cameras are served by the stateless batched ops only.
+inline bool tracker_capable(const pam_config& p) { return p.num_cameras <= PAM_MAX_V; }
+
 inline int make_devcfg(const pam_config& p, DevCfg& c, std::string& err) {
     auto bad = [&](const char* m) { err = m; return (int)PAM_E_INVALID; };
-    if (p.num_cameras < 1 || p.num_cameras > PAM_MAX_V) return bad("num_cameras outside 1..8");
+    if (p.num_cameras < 1 || p.num_cameras > 32) return bad("num_cameras outside 1..32");
     if (p.num_joints < 1 || p.num_joints > PAM_MAX_J) return bad("num_joints outside 1..32");
     if (p.max_detections < 1 || p.max_detections > PAM_MAX_D) return bad("max_detections outside 1..16");
     if (p.max_tracks < 1 || p.max_tracks > PAM_MAX_TRK) return bad("max_tracks outside 1..16");

@@ -80,6 +80,7 @@ struct TrackIO {
     float* out_joints;      // [S][T][MT][J][3]
     unsigned char* out_nv;  // [S][T][MT][J]
     int* out_assoc;         // [S][T][V][D]
+    int seq_frames;         // frames between consecutive sequences in every tensor above (>= T)
 };
 
 #define PAM_TRACK_THREADS_MAX 256
@@ -96,8 +97,8 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
     const int nfl_pad = (nfl + 3) / 4 * 4;
     float* dbuf = (float*)(arena + arena_doubles(c));
     int* cbuf = (int*)(dbuf + 2 * nfl_pad);
-    const float* gd = io.dets + (int64_t)s * T * nfl;
-    const int* gc = io.counts + (int64_t)s * T * c.V;
+    const float* gd = io.dets + (int64_t)s * io.seq_frames * nfl;
+    const int* gc = io.counts + (int64_t)s * io.seq_frames * c.V;
     if (T > 0) stage_frame(dbuf, cbuf, gd, gc, nfl, c.V);
     if (threadIdx.x == 0) carve(c, sh, arena);
     load_cameras(ctx, c, sh, cc);
@@ -112,7 +113,7 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
         if (t + 1 < T)
             stage_frame(dbuf + (cur ^ 1) * nfl_pad, cbuf + (cur ^ 1) * PAM_MAX_V, gd + (int64_t)(t + 1) * nfl,
                         gc + (t + 1) * c.V, nfl, c.V);
-        const int64_t ft = (int64_t)s * T + t;
+        const int64_t ft = (int64_t)s * io.seq_frames + t;
         FrameOut o;
         o.count = io.out_count ? io.out_count + ft : nullptr;
         o.ids = io.out_ids ? io.out_ids + ft * c.max_trk : nullptr;
@@ -166,7 +167,9 @@ struct pam_handle {
     // workspace of the *_host entry points
     DevBuf ws_state, ws_dets, ws_counts, ws_count, ws_ids, ws_joints, ws_nv, ws_assoc;
     int ws_S = 0;
-    cudaStream_t ws_stream = nullptr;
+    bool smem_opt_in = false;
+    cudaStream_t ws_stream = nullptr, ws_in = nullptr, ws_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_k;
     int64_t launches = 0;
     std::string err;
 };
@@ -243,6 +246,10 @@ int pam_destroy(pam_handle* h) {
     h->ws_state.release(); h->ws_dets.release(); h->ws_counts.release(); h->ws_count.release();
     h->ws_ids.release(); h->ws_joints.release(); h->ws_nv.release(); h->ws_assoc.release();
     if (h->ws_stream) cudaStreamDestroy(h->ws_stream);
+    if (h->ws_in) cudaStreamDestroy(h->ws_in);
+    if (h->ws_out) cudaStreamDestroy(h->ws_out);
+    for (auto e : h->ev_in) cudaEventDestroy(e);
+    for (auto e : h->ev_k) cudaEventDestroy(e);
     delete h;
     return PAM_OK;
 }
@@ -279,21 +286,29 @@ int pam_track_reset(pam_handle* h, void* d_state, int32_t S, void* stream) {
     return PAM_OK;
 }
 
+static int launch_track(pam_handle* h, void* d_state, int32_t S, int32_t T, int32_t frame0, const TrackIO& io,
+                        cudaStream_t stream) {
+    const size_t smem = track_smem_bytes(h->dc);
+    if (smem + sizeof(SeqShared) > 48 * 1024 && !h->smem_opt_in) {
+        CK(cudaFuncSetAttribute(k_track_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->smem_opt_in = true;
+    }
+    k_track_sequences<<<S, h->track_threads, smem, stream>>>(h->dc, h->cc, (char*)d_state, T, frame0, io);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return PAM_OK;
+}
+
 int pam_track_sequences(pam_handle* h, void* d_state, int32_t S, int32_t T, int32_t frame0, const float* d_dets,
                         const int32_t* d_counts, int32_t* d_out_count, int32_t* d_out_ids, float* d_out_joints,
                         uint8_t* d_out_nviews, int32_t* d_out_assoc, void* stream) {
     if (!h || !d_state || !d_dets || !d_counts || S < 0 || T < 0) return fail(h, PAM_E_INVALID, "bad argument");
     if (!h->have_cameras) return fail(h, PAM_E_NOCAMERAS, "pam_set_cameras has not been called");
+    if (!tracker_capable(h->cfg)) return fail(h, PAM_E_INVALID, "the stateful tracker handles at most 8 cameras");
     if (S == 0 || T == 0) return PAM_OK;
     CK(cudaSetDevice(h->device));
-    const size_t smem = track_smem_bytes(h->dc);
-    if (smem > 48 * 1024 - sizeof(SeqShared))
-        CK(cudaFuncSetAttribute(k_track_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TrackIO io{d_dets, d_counts, d_out_count, d_out_ids, d_out_joints, d_out_nviews, d_out_assoc};
-    k_track_sequences<<<S, h->track_threads, smem, (cudaStream_t)stream>>>(h->dc, h->cc, (char*)d_state, T, frame0, io);
-    h->launches += 1;
-    CK(cudaGetLastError());
-    return PAM_OK;
+    TrackIO io{d_dets, d_counts, d_out_count, d_out_ids, d_out_joints, d_out_nviews, d_out_assoc, T};
+    return launch_track(h, d_state, S, T, frame0, io, (cudaStream_t)stream);
 }
 
 int pam_track_status(pam_handle* h, const void* d_state, int32_t S, int32_t* h_status, void* stream) {
@@ -325,6 +340,7 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
                              uint8_t* h_out_nviews, int32_t* h_out_assoc) {
     if (!h || !h_dets || !h_counts || !h_out_count || S <= 0 || T <= 0) return fail(h, PAM_E_INVALID, "bad argument");
     if (!h->have_cameras) return fail(h, PAM_E_NOCAMERAS, "pam_set_cameras has not been called");
+    if (!tracker_capable(h->cfg)) return fail(h, PAM_E_INVALID, "the stateful tracker handles at most 8 cameras");
     CK(cudaSetDevice(h->device));
     if (!h->ws_stream) CK(cudaStreamCreateWithFlags(&h->ws_stream, cudaStreamNonBlocking));
     cudaStream_t st = h->ws_stream;
@@ -345,19 +361,52 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
     if (h_out_joints) CK(h->ws_joints.reserve(b_joints));
     if (h_out_nviews) CK(h->ws_nv.reserve(b_nv));
     if (h_out_assoc) CK(h->ws_assoc.reserve(b_assoc));
-    CK(cudaMemcpyAsync(h->ws_dets.p, h_dets, b_dets, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->ws_counts.p, h_counts, b_counts, cudaMemcpyHostToDevice, st));
-    int rc = pam_track_sequences(h, h->ws_state.p, S, T, frame0, (const float*)h->ws_dets.p, (const int32_t*)h->ws_counts.p,
-                                 (int32_t*)h->ws_count.p, h_out_ids ? (int32_t*)h->ws_ids.p : nullptr,
-                                 h_out_joints ? (float*)h->ws_joints.p : nullptr,
-                                 h_out_nviews ? (uint8_t*)h->ws_nv.p : nullptr,
-                                 h_out_assoc ? (int32_t*)h->ws_assoc.p : nullptr, st);
-    if (rc != PAM_OK) return rc;
-    CK(cudaMemcpyAsync(h_out_count, h->ws_count.p, b_count, cudaMemcpyDeviceToHost, st));
-    if (h_out_ids) CK(cudaMemcpyAsync(h_out_ids, h->ws_ids.p, b_ids, cudaMemcpyDeviceToHost, st));
-    if (h_out_joints) CK(cudaMemcpyAsync(h_out_joints, h->ws_joints.p, b_joints, cudaMemcpyDeviceToHost, st));
-    if (h_out_nviews) CK(cudaMemcpyAsync(h_out_nviews, h->ws_nv.p, b_nv, cudaMemcpyDeviceToHost, st));
-    if (h_out_assoc) CK(cudaMemcpyAsync(h_out_assoc, h->ws_assoc.p, b_assoc, cudaMemcpyDeviceToHost, st));
+    // Pipeline over chunks of frames: the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap
+    // the kernel of chunk k (three streams; tracker state stays in HBM between the chunk launches).
+    if (!h->ws_in) CK(cudaStreamCreateWithFlags(&h->ws_in, cudaStreamNonBlocking));
+    if (!h->ws_out) CK(cudaStreamCreateWithFlags(&h->ws_out, cudaStreamNonBlocking));
+    int nchunks = T / 256;
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > 16) nchunks = 16;
+    while ((int)h->ev_in.size() < nchunks + 1) {
+        cudaEvent_t e1, e2;
+        CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        h->ev_in.push_back(e1); h->ev_k.push_back(e2);
+    }
+    // the first H2D copy must not overtake earlier work queued on the compute stream (state reset)
+    CK(cudaEventRecord(h->ev_k[nchunks], st));
+    CK(cudaStreamWaitEvent(h->ws_in, h->ev_k[nchunks], 0));
+    const size_t f_dets = (size_t)c.V * c.D * c.J * 3 * 4, f_counts = (size_t)c.V * 4, f_count = 4;
+    const size_t f_ids = (size_t)c.max_trk * 4, f_joints = (size_t)c.max_trk * c.J * 3 * 4, f_nv = (size_t)c.max_trk * c.J;
+    const size_t f_assoc = (size_t)c.V * c.D * 4;
+    auto chunk2d = [&](void* dst, const void* src, size_t fbytes, int t0, int n, cudaMemcpyKind kind, cudaStream_t sx) {
+        return cudaMemcpy2DAsync((char*)dst + (size_t)t0 * fbytes, (size_t)T * fbytes, (const char*)src + (size_t)t0 * fbytes,
+                                 (size_t)T * fbytes, (size_t)n * fbytes, (size_t)S, kind, sx);
+    };
+    for (int k = 0; k < nchunks; ++k) {
+        const int t0 = (int)((int64_t)T * k / nchunks), t1 = (int)((int64_t)T * (k + 1) / nchunks), n = t1 - t0;
+        CK(chunk2d(h->ws_dets.p, h_dets, f_dets, t0, n, cudaMemcpyHostToDevice, h->ws_in));
+        CK(chunk2d(h->ws_counts.p, h_counts, f_counts, t0, n, cudaMemcpyHostToDevice, h->ws_in));
+        CK(cudaEventRecord(h->ev_in[k], h->ws_in));
+        CK(cudaStreamWaitEvent(st, h->ev_in[k], 0));
+        TrackIO io{(const float*)h->ws_dets.p + (size_t)t0 * (f_dets / 4), (const int32_t*)h->ws_counts.p + (size_t)t0 * c.V,
+                   (int32_t*)h->ws_count.p + t0,
+                   h_out_ids ? (int32_t*)h->ws_ids.p + (size_t)t0 * c.max_trk : nullptr,
+                   h_out_joints ? (float*)h->ws_joints.p + (size_t)t0 * (f_joints / 4) : nullptr,
+                   h_out_nviews ? (uint8_t*)h->ws_nv.p + (size_t)t0 * f_nv : nullptr,
+                   h_out_assoc ? (int32_t*)h->ws_assoc.p + (size_t)t0 * (f_assoc / 4) : nullptr, T};
+        int rc = launch_track(h, h->ws_state.p, S, n, frame0 + t0, io, st);
+        if (rc != PAM_OK) return rc;
+        CK(cudaEventRecord(h->ev_k[k], st));
+        CK(cudaStreamWaitEvent(h->ws_out, h->ev_k[k], 0));
+        CK(chunk2d(h_out_count, h->ws_count.p, f_count, t0, n, cudaMemcpyDeviceToHost, h->ws_out));
+        if (h_out_ids) CK(chunk2d(h_out_ids, h->ws_ids.p, f_ids, t0, n, cudaMemcpyDeviceToHost, h->ws_out));
+        if (h_out_joints) CK(chunk2d(h_out_joints, h->ws_joints.p, f_joints, t0, n, cudaMemcpyDeviceToHost, h->ws_out));
+        if (h_out_nviews) CK(chunk2d(h_out_nviews, h->ws_nv.p, f_nv, t0, n, cudaMemcpyDeviceToHost, h->ws_out));
+        if (h_out_assoc) CK(chunk2d(h_out_assoc, h->ws_assoc.p, f_assoc, t0, n, cudaMemcpyDeviceToHost, h->ws_out));
+    }
+    CK(cudaStreamSynchronize(h->ws_out));
     return pam_track_status(h, h->ws_state.p, S, nullptr, st);
 }
 

@@ -1,1 +1,294 @@
-// stateless batched ops (filled in below)
+// pam_ops.cuh -- stateless batched kernels: one kernel per reference function of SURVEY.md
+// section 8a that is callable on its own (the drop-in modules matching / construction / calculate
+// bind to these through the C ABI).  All arithmetic is FP64 on the reference's float32 camera
+// constants; any number of cameras up to PAM_OPS_MAX_V.
+//
+//   k_project_points      Camera.projectPoints_parallel                 ivclabpose.py:91-98
+//   k_assoc_affinity      association block of tracking()               tracking/IterativeTracker.py:137-149
+//   k_assign              scipy linear_sum_assignment (batched)         tracking/IterativeTracker.py:79,150
+//   k_epipolar_pairs      epipolar_affinity_parallel                    utils/matching.py:115-151
+//   k_epipolar_allpairs   epipolar_affinity (+ epipolar_distance)       utils/matching.py:50-113
+//   k_view_filter         Greedy_matching, modes 'update' / 'init'      utils/matching.py:243-295
+//   k_triangulate         SVD_pose_kernel_jf / _parallel / SVD_pose_kernel   utils/construction.py:64-131
+//   k_ray_distance        back_project_ray + line2point_distance_3D     utils/matching.py:10-17, utils/calculate.py:26-32
+//   k_epipolar_distance   epipolar_distance (pairwise, both directions) utils/matching.py:50-91
+#pragma once
+#include "pam_core.h"
+
+#define PAM_OPS_MAX_V 32
+#define PAM_OPS_MAX_N 64   // assignment problems up to 64 x 64
+
+namespace pam {
+
+__device__ __forceinline__ void load9(const float* __restrict__ src, double* dst) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dst[k] = (double)__ldg(src + k);
+}
+__device__ __forceinline__ void load12(const float* __restrict__ src, double* dst) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) dst[k] = (double)__ldg(src + k);
+}
+
+// ---- a2: (n, J, 3) world joints -> (V, n, J, 2) pixels (v, u) ------------------------------------
+__global__ void k_project_points(const float* __restrict__ P, int V, const double* __restrict__ X, int N,
+                                 double* __restrict__ out) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= V * N) return;
+    const int cam = it / N, p = it - cam * N;
+    double Pm[12];
+    load12(P + cam * 12, Pm);
+    const double x = X[p * 3], y = X[p * 3 + 1], z = X[p * 3 + 2];
+    const double a = Pm[0] * x + Pm[1] * y + Pm[2] * z + Pm[3];
+    const double b = Pm[4] * x + Pm[5] * y + Pm[6] * z + Pm[7];
+    const double w = Pm[8] * x + Pm[9] * y + Pm[10] * z + Pm[11];
+    out[(int64_t)it * 2 + 0] = b / w;
+    out[(int64_t)it * 2 + 1] = a / w;
+}
+
+// ---- a3: affinity of every (camera, track, detection) ---------------------------------------------
+// tracks X [n][J][3], dt [n]; dets [V][mmax][J][3] f64 (v,u,conf), counts [V]; aff [V][n][mmax]
+__global__ void k_assoc_affinity(const float* __restrict__ P, int V, const double* __restrict__ X,
+                                 const int* __restrict__ dt, const double* __restrict__ dets,
+                                 const int* __restrict__ counts, int n, int mmax, int J, double alpha2d,
+                                 double lambda_a, int min_valid, double* __restrict__ aff) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= V * n * mmax) return;
+    const int cam = it / (n * mmax), rem = it - cam * (n * mmax), i = rem / mmax, d = rem - i * mmax;
+    if (d >= counts[cam]) { aff[it] = 0.0; return; }
+    double Pm[12];
+    load12(P + cam * 12, Pm);
+    const double* q = dets + ((int64_t)(cam * mmax + d) * J) * 3;
+    const double* Xi = X + (int64_t)i * J * 3;
+    const double denom = alpha2d * (double)dt[i];
+    double sum = 0.0;
+    int cnt = 0;
+    for (int j = 0; j < J; ++j) {
+        const double x = Xi[j * 3], y = Xi[j * 3 + 1], z = Xi[j * 3 + 2];
+        const double a = Pm[0] * x + Pm[1] * y + Pm[2] * z + Pm[3];
+        const double b = Pm[4] * x + Pm[5] * y + Pm[6] * z + Pm[7];
+        const double w = Pm[8] * x + Pm[9] * y + Pm[10] * z + Pm[11];
+        const double dv = b / w - q[j * 3 + 0], du = a / w - q[j * 3 + 1];
+        const double cj = 1.0 - sqrt(dv * dv + du * du) / denom;
+        if (cj > 0.0) { sum += cj; ++cnt; }
+    }
+    double r = (cnt > min_valid) ? sum / (double)cnt : 0.0;
+    r = r / exp(lambda_a * (double)dt[i]);
+    if (r != r) r = 0.0;
+    aff[it] = r;
+}
+
+// ---- a4: batched rectangular assignment; one thread per problem ----------------------------------
+__global__ void k_assign(const double* __restrict__ cost, int B, int nr, int nc, int maximize, int* __restrict__ col4row) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double* C = cost + (int64_t)b * nr * nc;
+    const double sgn = maximize ? -1.0 : 1.0;
+    int out[PAM_OPS_MAX_N];
+    lsap_solve<PAM_OPS_MAX_N>(nr, nc, [&](int i, int j) { return sgn * C[i * nc + j]; }, out);
+    for (int i = 0; i < nr; ++i) col4row[(int64_t)b * nr + i] = out[i];
+}
+
+// ---- a6: symmetric point-to-epipolar-line distances, float64 form ----------------------------------
+// pose [M][J][3] (v,u,conf), cam [M]; D [M][M][J], mean [M][M]; same-camera pairs use F = 0.
+__global__ void k_epipolar_pairs(const float* __restrict__ F, int V, const double* __restrict__ pose,
+                                 const int* __restrict__ cam, int M, int J, double* __restrict__ D,
+                                 double* __restrict__ mean) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= M * M) return;
+    const int a = it / M, b = it - a * M;
+    if (a > b) return;                        // the (a, b) thread writes both triangles
+    const int ca = cam[a], cb = cam[b];
+    double Fab[9], Fba[9];
+    if (ca == cb) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { Fab[k] = 0.0; Fba[k] = 0.0; }
+    } else {
+        load9(F + ((int64_t)ca * V + cb) * 9, Fab);
+        load9(F + ((int64_t)cb * V + ca) * 9, Fba);
+    }
+    const double* pa = pose + (int64_t)a * J * 3;
+    const double* pb = pose + (int64_t)b * J * 3;
+    double vals[PAM_MAX_J];
+    for (int j = 0; j < J; ++j) {
+        const double va = pa[j * 3], ua = pa[j * 3 + 1], vb = pb[j * 3], ub = pb[j * 3 + 1];
+        const double dab = epi_dist_f64(Fab, ua, va, ub, vb);
+        const double dba = epi_dist_f64(Fba, ub, vb, ua, va);
+        const double d = (dab + dba) / 2.0;
+        vals[j] = d;
+        D[((int64_t)a * M + b) * J + j] = d;
+        D[((int64_t)b * M + a) * J + j] = d;
+    }
+    const double m = np_sum(vals, J) / (double)J;
+    mean[(int64_t)a * M + b] = m;
+    mean[(int64_t)b * M + a] = m;
+}
+
+// ---- a7: all-pairs form with float32 stores (dense crowd) ------------------------------------------
+// One CTA = a TILE x TILE block of detection pairs; both pose tiles are staged in shared memory as
+// (u, v) pairs; each thread walks the joints of its pairs.  aff [M][M] f32 (25 between detections
+// of one camera, 0 on the diagonal), D [M][M][J] f32 or null.
+#define PAM_AP_TILE 32
+__global__ void __launch_bounds__(256)
+k_epipolar_allpairs(const float* __restrict__ F, int V, const double* __restrict__ pose, const int* __restrict__ cam,
+                    int M, int J, float* __restrict__ aff, float* __restrict__ D) {
+    extern __shared__ double tile[];           // [2][TILE][J][2]
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    if (tj < ti) return;                       // upper-triangular tiles only; results are mirrored
+    double* A = tile;
+    double* Bt = tile + PAM_AP_TILE * J * 2;
+    for (int e = threadIdx.x; e < PAM_AP_TILE * J; e += blockDim.x) {
+        const int r = e / J, j = e - r * J;
+        const int ia = ti * PAM_AP_TILE + r, ib = tj * PAM_AP_TILE + r;
+        if (ia < M) { A[e * 2] = pose[((int64_t)ia * J + j) * 3 + 1]; A[e * 2 + 1] = pose[((int64_t)ia * J + j) * 3]; }
+        if (ib < M) { Bt[e * 2] = pose[((int64_t)ib * J + j) * 3 + 1]; Bt[e * 2 + 1] = pose[((int64_t)ib * J + j) * 3]; }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < PAM_AP_TILE * PAM_AP_TILE; p += blockDim.x) {
+        const int r = p / PAM_AP_TILE, cidx = p - r * PAM_AP_TILE;
+        const int i = ti * PAM_AP_TILE + r, j2 = tj * PAM_AP_TILE + cidx;
+        if (i >= M || j2 >= M || j2 < i) continue;
+        if (i == j2) {
+            aff[(int64_t)i * M + i] = 0.0f;
+            if (D) for (int j = 0; j < J; ++j) D[((int64_t)i * M + i) * J + j] = 0.0f;
+            continue;
+        }
+        const int ci = cam[i], cj = cam[j2];
+        if (ci == cj) {
+            aff[(int64_t)i * M + j2] = 25.0f; aff[(int64_t)j2 * M + i] = 25.0f;
+            if (D) for (int j = 0; j < J; ++j) { D[((int64_t)i * M + j2) * J + j] = 0.0f; D[((int64_t)j2 * M + i) * J + j] = 0.0f; }
+            continue;
+        }
+        double Fm[9];
+        load9(F + ((int64_t)ci * V + cj) * 9, Fm);
+        const double* xa = A + (int64_t)r * J * 2;
+        const double* xb = Bt + (int64_t)cidx * J * 2;
+        NpSumStream<double> acc;
+        acc.begin(J);
+        for (int j = 0; j < J; ++j) {
+            double d1, d2;
+            epi_pair_cv(Fm, xa[j * 2], xa[j * 2 + 1], xb[j * 2], xb[j * 2 + 1], d1, d2);
+            const double sym = (d1 + d2) / 2.0;
+            acc.push(sym);
+            if (D) { D[((int64_t)i * M + j2) * J + j] = (float)sym; D[((int64_t)j2 * M + i) * J + j] = (float)sym; }
+        }
+        const float m = (float)(acc.total() / (double)J);
+        aff[(int64_t)i * M + j2] = m;
+        aff[(int64_t)j2 * M + i] = m;
+    }
+}
+
+// ---- a8 / a17: part-aware view filter on given affinity matrices -----------------------------------
+// B problems of Vt views: A [B][Vt][Vt] (f64, or f32 values widened by the caller for 'init'),
+// uv [B][Vt][2] (u, v), cam [Vt], next [B][3]  ->  keep [B][Vt] (0/1).  mode 0 = update, 1 = init.
+__global__ void k_view_filter(const float* __restrict__ RKinv, const double* __restrict__ pos,
+                              const double* __restrict__ A, const float* __restrict__ Af, const double* __restrict__ uv,
+                              const int* __restrict__ cam, const double* __restrict__ next, int B, int Vt, int mode,
+                              unsigned char* __restrict__ keep) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    uint32_t alive = (Vt >= 32) ? 0xffffffffu : ((1u << Vt) - 1u);
+    if (mode == 0) {
+        const double* Ab = A + (int64_t)b * Vt * Vt;
+        double rd[PAM_OPS_MAX_V];
+        for (int a = 0; a < Vt; ++a) rd[a] = 0.0;
+        for (int r = 0; r < Vt; ++r)
+            for (int c2 = r; c2 < Vt; ++c2) {
+                if (!(Ab[r * Vt + c2] < 0.0)) continue;
+                if (!((alive >> r) & 1u) || !((alive >> c2) & 1u)) continue;
+                for (int s = 0; s < 2; ++s) {
+                    const int k = s ? c2 : r;
+                    if (rd[k] == 0.0) {
+                        double RK[9], pc[3] = {pos[cam[k] * 3], pos[cam[k] * 3 + 1], pos[cam[k] * 3 + 2]};
+                        load9(RKinv + cam[k] * 9, RK);
+                        rd[k] = ray_point_distance(RK, pc, uv[((int64_t)b * Vt + k) * 2], uv[((int64_t)b * Vt + k) * 2 + 1],
+                                                   next + (int64_t)b * 3);
+                    }
+                }
+                if (rd[r] > rd[c2]) alive &= ~(1u << r); else alive &= ~(1u << c2);
+            }
+    } else {
+        const float* Ab = Af + (int64_t)b * Vt * Vt;
+        for (int r = 0; r < Vt; ++r)
+            for (int c2 = r; c2 < Vt; ++c2) {
+                if (!(Ab[r * Vt + c2] < 0.0f)) continue;
+                if (!((alive >> r) & 1u) || !((alive >> c2) & 1u)) continue;
+                const float s1 = np_sum(Ab + r * Vt, Vt), s2 = np_sum(Ab + c2 * Vt, Vt);
+                if (s1 > s2) alive &= ~(1u << c2); else alive &= ~(1u << r);
+            }
+    }
+    for (int a = 0; a < Vt; ++a) keep[(int64_t)b * Vt + a] = (alive >> a) & 1u;
+}
+
+// ---- a10 / a11: weighted DLT of B x J joints over Vt views -------------------------------------------
+// pose [B][Vt][J][3] (v,u,conf), cam [B][Vt], w [B][Vt] = exp(-lambda_t T), keep [B][J][Vt] or null,
+// next [B][J][3] or null (used when < 2 views survive; NaN if null)  ->  out [B][J][3]
+__global__ void k_triangulate(const float* __restrict__ P, const double* __restrict__ pose, const int* __restrict__ cam,
+                              const double* __restrict__ w, const unsigned char* __restrict__ keep,
+                              const double* __restrict__ next, int B, int Vt, int J, double* __restrict__ out) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= B * J) return;
+    const int b = it / J, j = it - b * J;
+    const unsigned char* kp = keep ? keep + (int64_t)it * Vt : nullptr;
+    int nv = 0;
+    bool fresh = true;
+    for (int a = 0; a < Vt; ++a) {
+        if (kp && !kp[a]) continue;
+        ++nv;
+        if (w[(int64_t)b * Vt + a] != 1.0) fresh = false;
+    }
+    double* o = out + (int64_t)it * 3;
+    if (nv < 2) {
+        if (next) { o[0] = next[(int64_t)it * 3]; o[1] = next[(int64_t)it * 3 + 1]; o[2] = next[(int64_t)it * 3 + 2]; }
+        else { o[0] = o[1] = o[2] = nan(""); }
+        return;
+    }
+    DltAccum acc;
+    int path = -1;
+    for (int pass = fresh ? 0 : 1; pass < 2 && path < 0; ++pass) {
+        acc.reset(pass == 0);
+        for (int a = 0; a < Vt; ++a) {
+            if (kp && !kp[a]) continue;
+            double Pm[12];
+            load12(P + cam[(int64_t)b * Vt + a] * 12, Pm);
+            const double* q = pose + (((int64_t)b * Vt + a) * J + j) * 3;
+            acc.add_view(Pm, q[1], q[0], w[(int64_t)b * Vt + a]);
+        }
+        acc.solve(o, &path);
+    }
+}
+
+// ---- a9: distance of 3-D points to back-projected pixel rays ---------------------------------------
+// uv [n][2] (u, v), X [n][3] -> dist [n], dirs [n][3] (unit) for camera `cam`
+__global__ void k_ray_distance(const float* __restrict__ RKinv, const double* __restrict__ pos, int cam,
+                               const double* __restrict__ uv, const double* __restrict__ X, int n,
+                               double* __restrict__ dist, double* __restrict__ dirs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double RK[9], pc[3] = {pos[cam * 3], pos[cam * 3 + 1], pos[cam * 3 + 2]};
+    load9(RKinv + cam * 9, RK);
+    const double u = uv[i * 2], v = uv[i * 2 + 1];
+    if (dirs) {
+        double d0 = RK[0] * u + RK[1] * v + RK[2], d1 = RK[3] * u + RK[4] * v + RK[5], d2 = RK[6] * u + RK[7] * v + RK[8];
+        const double inv = 1.0 / sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        dirs[i * 3] = d0 * inv; dirs[i * 3 + 1] = d1 * inv; dirs[i * 3 + 2] = d2 * inv;
+    }
+    if (dist && X) dist[i] = ray_point_distance(RK, pc, u, v, X + (int64_t)i * 3);
+}
+
+// ---- a7 (pairwise form): epipolar_distance(cam1, person1, cam2, person2) -> (n, 2) -----------------
+// B pairs of poses: p1 [B][J][3], p2 [B][J][3] with cameras c1[B], c2[B] -> out [B][J][2]
+__global__ void k_epipolar_distance(const float* __restrict__ F, int V, const double* __restrict__ p1,
+                                    const double* __restrict__ p2, const int* __restrict__ c1, const int* __restrict__ c2,
+                                    int B, int J, double* __restrict__ out) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= B * J) return;
+    const int b = it / J;
+    double Fm[9];
+    load9(F + ((int64_t)c1[b] * V + c2[b]) * 9, Fm);
+    double d1, d2;
+    epi_pair_cv(Fm, p1[(int64_t)it * 3 + 1], p1[(int64_t)it * 3], p2[(int64_t)it * 3 + 1], p2[(int64_t)it * 3], d1, d2);
+    out[(int64_t)it * 2] = d1;
+    out[(int64_t)it * 2 + 1] = d2;
+}
+
+}  // namespace pam

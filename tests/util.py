@@ -75,3 +75,64 @@ def compare_with_oracle(out, s, stream, oracle_out, oracle_assoc, tol_abs=5e-4, 
             for c, a in enumerate(oracle_assoc[t]):
                 assert np.array_equal(out["assoc"][s, t, c, :len(a)], a), f"frame {t} cam {c}: association differs"
     return worst
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors + drop-in module loading
+# ------------------------------------------------------------------------------------------------
+import os as _os
+import sys as _sys
+
+GOLDEN = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+
+
+def golden_streams():
+    z = np.load(_os.path.join(GOLDEN, "streams.npz"))
+    out = []
+    for n in range(int(z["n_streams"])):
+        p = f"s{n}_"
+        shape = synth.SHAPES[str(z[p + "shape"])]
+        rig = dict(P=z[p + "P"], K=z[p + "K"], RT=z[p + "RT"], width=shape.width, height=shape.height)
+        st = synth.Stream(shape, -1, rig, z[p + "dets"], z[p + "counts"], None, None)
+        out.append((st, {k: z[p + k] for k in ("count", "ids", "joints", "views", "assoc")}))
+    return out
+
+
+def golden_as_oracle_lists(g):
+    """Golden arrays -> the per-frame lists compare_with_oracle() expects."""
+    T = len(g["count"])
+    frames = [(g["ids"][t, :g["count"][t]], g["joints"][t, :g["count"][t]], g["views"][t, :g["count"][t]]) for t in range(T)]
+    assoc = [[g["assoc"][t, c] for c in range(g["assoc"].shape[1])] for t in range(T)]
+    return frames, assoc
+
+
+def golden_functions():
+    return np.load(_os.path.join(GOLDEN, "functions.npz"))
+
+
+def load_dropin():
+    """Import the flat drop-in modules (calculate, matching, construction, hypothesis,
+    IterativeTracker) without leaving them in sys.modules under those generic names (pytest's
+    own `hypothesis` plugin uses one of them)."""
+    import importlib.util
+    import types
+    from pam_b200 import dropin
+    here = dropin.install()
+    names = ["_pkg", "calculate", "matching", "construction", "hypothesis", "IterativeTracker"]
+    saved = {k: _sys.modules.get(k) for k in names}
+    ns = types.SimpleNamespace()
+    try:
+        for k in names:
+            _sys.modules.pop(k, None)
+        for k in names:
+            spec = importlib.util.spec_from_file_location(k, _os.path.join(here, k + ".py"))
+            mod = importlib.util.module_from_spec(spec)
+            _sys.modules[k] = mod
+            spec.loader.exec_module(mod)
+            setattr(ns, k, mod)
+    finally:
+        for k in names:
+            _sys.modules.pop(k, None)
+            if saved[k] is not None:
+                _sys.modules[k] = saved[k]
+    return ns
