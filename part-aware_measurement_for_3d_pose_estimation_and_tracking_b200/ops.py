@@ -109,8 +109,8 @@ class GeometryOps:
                 dets[c, :len(d)] = np.asarray(d, dtype=np.float64)
         X = self._dev(np.asarray(tracks3d, dtype=np.float64), torch.float64)
         aff = torch.empty((self.V, n, mmax), dtype=torch.float64, device=self.dev)
-        self._call(self.lib.pam_assoc_affinity, self._p(X), self._p(self._dev(np.asarray(dt), torch.int32)),
-                   self._p(self._dev(dets, torch.float64)), self._p(self._dev(counts, torch.int32)), n, mmax,
+        d_dt, d_dets, d_counts = self._dev(np.asarray(dt), torch.int32), self._dev(dets, torch.float64), self._dev(counts, torch.int32)
+        self._call(self.lib.pam_assoc_affinity, self._p(X), self._p(d_dt), self._p(d_dets), self._p(d_counts), n, mmax,
                    self._p(aff), self._stream())
         if not as_numpy:
             return aff, counts
@@ -128,8 +128,8 @@ class GeometryOps:
         B, nr, nc = cb.shape
         out = torch.full((B, max(nr, 1)), -1, dtype=torch.int32, device=self.dev)
         if nr and nc:
-            self._call(self.lib.pam_assign, self._p(self._dev(cb, torch.float64)), B, nr, nc, 1 if maximize else 0,
-                       self._p(out), self._stream())
+            d_cost = self._dev(cb, torch.float64)
+            self._call(self.lib.pam_assign, self._p(d_cost), B, nr, nc, 1 if maximize else 0, self._p(out), self._stream())
         o = out.cpu().numpy()
         res = []
         for b in range(B):
@@ -145,8 +145,8 @@ class GeometryOps:
         M = pose.shape[0]
         D = torch.empty((M, M, self.J), dtype=torch.float64, device=self.dev)
         mean = torch.empty((M, M), dtype=torch.float64, device=self.dev)
-        self._call(self.lib.pam_epipolar_pairs, self._p(pose), self._p(self._dev(np.asarray(cam_index), torch.int32)),
-                   M, self._p(D), self._p(mean), self._stream())
+        d_cam = self._dev(np.asarray(cam_index), torch.int32)
+        self._call(self.lib.pam_epipolar_pairs, self._p(pose), self._p(d_cam), M, self._p(D), self._p(mean), self._stream())
         return (mean.cpu().numpy(), D.cpu().numpy()) if as_numpy else (mean, D)
 
     def epipolar_allpairs(self, cam_index, pose_mat, want_dist=True, as_numpy=True):
@@ -157,9 +157,8 @@ class GeometryOps:
         M = pose.shape[0]
         aff = torch.empty((M, M), dtype=torch.float32, device=self.dev)
         D = torch.empty((M, M, self.J), dtype=torch.float32, device=self.dev) if want_dist else None
-        cam = cam_index if isinstance(cam_index, torch.Tensor) else np.asarray(cam_index)
-        self._call(self.lib.pam_epipolar_allpairs, self._p(pose), self._p(self._dev(cam, torch.int32)), M,
-                   self._p(aff), self._p(D), self._stream())
+        d_cam = self._dev(cam_index if isinstance(cam_index, torch.Tensor) else np.asarray(cam_index), torch.int32)
+        self._call(self.lib.pam_epipolar_allpairs, self._p(pose), self._p(d_cam), M, self._p(aff), self._p(D), self._stream())
         if not as_numpy:
             return aff, D
         return aff.cpu().numpy(), (D.cpu().numpy() if D is not None else None)
@@ -171,9 +170,9 @@ class GeometryOps:
         p2 = self._dev(np.asarray(pose2, dtype=np.float64), torch.float64)
         B = p1.shape[0]
         out = torch.empty((B, self.J, 2), dtype=torch.float64, device=self.dev)
-        self._call(self.lib.pam_epipolar_distance, self._p(p1), self._p(p2),
-                   self._p(self._dev(np.asarray(cam1), torch.int32)), self._p(self._dev(np.asarray(cam2), torch.int32)),
-                   B, self._p(out), self._stream())
+        d_c1, d_c2 = self._dev(np.asarray(cam1), torch.int32), self._dev(np.asarray(cam2), torch.int32)
+        self._call(self.lib.pam_epipolar_distance, self._p(p1), self._p(p2), self._p(d_c1), self._p(d_c2), B, self._p(out),
+                   self._stream())
         return out.cpu().numpy()
 
     # -- a8 / a17 --------------------------------------------------------------------------------
@@ -186,13 +185,15 @@ class GeometryOps:
         keep = torch.empty((B, n), dtype=torch.uint8, device=self.dev)
         cam = self._dev(np.asarray(cam_index), torch.int32)
         if mode == "update":
-            self._call(self.lib.pam_view_filter, 0, self._p(self._dev(A.astype(np.float64), torch.float64)), None,
-                       self._p(self._dev(np.asarray(uv, dtype=np.float64), torch.float64)), self._p(cam),
-                       self._p(self._dev(np.asarray(next_pose, dtype=np.float64), torch.float64)), B, n, self._p(keep),
-                       self._stream())
+            d_A = self._dev(A.astype(np.float64), torch.float64)
+            d_uv = self._dev(np.asarray(uv, dtype=np.float64), torch.float64)
+            d_next = self._dev(np.asarray(next_pose, dtype=np.float64), torch.float64)
+            self._call(self.lib.pam_view_filter, 0, self._p(d_A), None, self._p(d_uv), self._p(cam), self._p(d_next), B, n,
+                       self._p(keep), self._stream())
         else:
-            self._call(self.lib.pam_view_filter, 1, None, self._p(self._dev(A.astype(np.float32), torch.float32)), None,
-                       self._p(cam), None, B, n, self._p(keep), self._stream())
+            d_A = self._dev(A.astype(np.float32), torch.float32)
+            self._call(self.lib.pam_view_filter, 1, None, self._p(d_A), None, self._p(cam), None, B, n, self._p(keep),
+                       self._stream())
         return keep.cpu().numpy()
 
     # -- a10 / a11 -------------------------------------------------------------------------------

@@ -117,7 +117,7 @@ def load_dropin():
     import importlib.util
     import types
     from pam_b200 import dropin
-    here = dropin.install()
+    here = _os.path.dirname(_os.path.abspath(dropin.__file__))   # not dropin.install(): keep sys.path clean
     names = ["_pkg", "calculate", "matching", "construction", "hypothesis", "IterativeTracker"]
     saved = {k: _sys.modules.get(k) for k in names}
     ns = types.SimpleNamespace()
