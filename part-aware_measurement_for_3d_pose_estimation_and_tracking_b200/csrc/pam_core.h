@@ -28,6 +28,15 @@
 #define PAM_HD_NOINLINE
 #endif
 
+// The tracker kernel is a long straight-line program executed once per frame; keeping its hot part
+// inside the 32 KB L1.5 instruction cache matters more than saving loop overhead, so loops with
+// run-time trip counts are kept rolled.
+#if defined(__CUDACC__)
+#define PAM_NOUNROLL _Pragma("unroll 1")
+#else
+#define PAM_NOUNROLL
+#endif
+
 #define PAM_MAX_V 8        // cameras per rig handled by the stateful tracker
 #define PAM_MAX_TRK 16     // track slots per sequence
 #define PAM_MAX_D 16       // detections per camera per frame
@@ -39,6 +48,14 @@
 
 namespace pam {
 
+PAM_HD int popcount32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------
 // numpy reduction order
 // ------------------------------------------------------------------------------------------
@@ -47,20 +64,20 @@ template <class T>
 PAM_HD T np_sum(const T* a, int n, int stride = 1) {
     if (n < 8) {
         T r = (T)0;
-        for (int i = 0; i < n; ++i) r += a[i * stride];
+        PAM_NOUNROLL for (int i = 0; i < n; ++i) r += a[i * stride];
         return r;
     }
     T r0 = a[0], r1 = a[stride], r2 = a[2 * stride], r3 = a[3 * stride];
     T r4 = a[4 * stride], r5 = a[5 * stride], r6 = a[6 * stride], r7 = a[7 * stride];
     int i = 8;
-    for (; i < n - (n % 8); i += 8) {
+    PAM_NOUNROLL for (; i < n - (n % 8); i += 8) {
         r0 += a[(i + 0) * stride]; r1 += a[(i + 1) * stride];
         r2 += a[(i + 2) * stride]; r3 += a[(i + 3) * stride];
         r4 += a[(i + 4) * stride]; r5 += a[(i + 5) * stride];
         r6 += a[(i + 6) * stride]; r7 += a[(i + 7) * stride];
     }
     T res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
-    for (; i < n; ++i) res += a[i * stride];
+    PAM_NOUNROLL for (; i < n; ++i) res += a[i * stride];
     return res;
 }
 
@@ -92,13 +109,47 @@ struct NpSumStream {
 // ------------------------------------------------------------------------------------------
 // F is the 3x3 (row-major) fundamental matrix cams[a].F[cid_b]:  x_a^T F x_b = 0,  x = (u, v, 1).
 
-// Reciprocal square root: one MUFU.RSQ64H seed + Newton steps on the device (cheaper than a
-// divide plus a square root), 1/sqrt on the host harness.
+// Short FP64 special functions for the device: one MUFU seed (rsqrt.approx / rcp.approx, ~2^-23..2^-26
+// relative) + two Newton steps = full double precision to 1-2 ulp in 5-9 instructions, versus the
+// 15-30 instructions (plus slow-path branches) of the IEEE-rounded library routines.  They keep the
+// hot loop small enough for the instruction cache.  Arguments are positive normal numbers wherever
+// these are used (squared pixel norms, homogeneous depths, pivots); the plain C versions serve the
+// host harness.
 PAM_HD double rsqrt_f64(double x) {
 #if defined(__CUDA_ARCH__)
-    return rsqrt(x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    return fma(y, e, y);
 #else
     return 1.0 / sqrt(x);
+#endif
+}
+PAM_HD double rcp_f64(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+#else
+    return 1.0 / x;
+#endif
+}
+// sqrt for x >= 0 (0 -> 0)
+PAM_HD double sqrt_f64(double x) {
+#if defined(__CUDA_ARCH__)
+    if (!(x > 0.0)) return 0.0;
+    const double y = rsqrt_f64(x);
+    double s = x * y;
+    const double r = fma(-s, s, x);
+    return fma(r, 0.5 * y, s);
+#else
+    return sqrt(x);
 #endif
 }
 
@@ -154,7 +205,7 @@ PAM_HD double ray_point_distance(const double* RK, const double* pos, double u, 
     double c0 = a1 * b2 - a2 * b1;
     double c1 = a2 * b0 - a0 * b2;
     double c2 = a0 * b1 - a1 * b0;
-    return sqrt((c0 * c0 + c1 * c1 + c2 * c2) / (a0 * a0 + a1 * a1 + a2 * a2));
+    return sqrt_f64((c0 * c0 + c1 * c1 + c2 * c2) * rcp_f64(a0 * a0 + a1 * a1 + a2 * a2));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -251,7 +302,7 @@ struct DltAccum {
     // inverse iteration on R^T R; x = homogeneous solution (unit norm).  false = not converged.
     PAM_HD bool invit(double* x) const {
         if (r00 == 0.0 || r11 == 0.0 || r22 == 0.0 || r33 == 0.0) return false;
-        const double i0 = 1.0 / r00, i1 = 1.0 / r11, i2 = 1.0 / r22, i3 = 1.0 / r33;
+        const double i0 = rcp_f64(r00), i1 = rcp_f64(r11), i2 = rcp_f64(r22), i3 = rcp_f64(r33);
         // start from R^-1 e4 (the direction R shrinks most when r33 is its smallest pivot)
         double x3 = 1.0;
         double x2 = -(r23 * x3) * i2;
@@ -260,7 +311,7 @@ struct DltAccum {
         double inv = rsqrt_f64(x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3);
         x0 *= inv; x1 *= inv; x2 *= inv; x3 *= inv;
         bool ok = false;
-        for (int it = 0; it < 8; ++it) {
+        PAM_NOUNROLL for (int it = 0; it < 8; ++it) {
             double y0 = x0 * i0;
             double y1 = (x1 - r01 * y0) * i1;
             double y2 = (x2 - r02 * y0 - r12 * y1) * i2;
@@ -284,63 +335,48 @@ struct DltAccum {
     // Columns are orthogonalised to |g_p . g_q| <= 1e-14 |g_p||g_q| (a relative criterion, so the
     // tiny singular values of stale-view systems are resolved as well as the large ones).
     PAM_HD_NOINLINE void jacobi(double* x) const {
+        // rare fallback: kept compact (rolled loops, arrays in local memory) to spare the instruction cache
         double g[4][4] = {{r00, r01, r02, r03}, {0.0, r11, r12, r13}, {0.0, 0.0, r22, r23}, {0.0, 0.0, 0.0, r33}};
         double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
         for (int sweep = 0; sweep < 10; ++sweep) {
             bool rotated = false;
 #if defined(__CUDA_ARCH__)
-#pragma unroll
+#pragma unroll 1
 #endif
-            for (int p = 0; p < 3; ++p) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                for (int q = p + 1; q < 4; ++q) {
-                    double al = 0.0, be = 0.0, ga = 0.0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                    for (int k = 0; k < 4; ++k) {
-                        al += g[k][p] * g[k][p];
-                        be += g[k][q] * g[k][q];
-                        ga += g[k][p] * g[k][q];
-                    }
-                    if (ga * ga <= 1e-28 * (al * be)) continue;
-                    rotated = true;
-                    // tan of the rotation angle: t = sign(tau) 2 ga / (|tau| + sqrt(tau^2 + 4 ga^2)), tau = be - al
-                    double tau = be - al, g2 = 2.0 * ga;
-                    double h = sqrt(tau * tau + g2 * g2);
-                    double t = g2 / ((tau < 0.0) ? (tau - h) : (tau + h));
-                    double c = rsqrt_f64(1.0 + t * t), s = c * t;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                    for (int k = 0; k < 4; ++k) {
-                        double gp = g[k][p], gq = g[k][q];
-                        g[k][p] = c * gp - s * gq;
-                        g[k][q] = s * gp + c * gq;
-                        double vp = V[k][p], vq = V[k][q];
-                        V[k][p] = c * vp - s * vq;
-                        V[k][q] = s * vp + c * vq;
-                    }
+            for (int pq = 0; pq < 6; ++pq) {
+                const int p = (pq < 3) ? 0 : ((pq < 5) ? 1 : 2);
+                const int q = (pq < 3) ? pq + 1 : ((pq < 5) ? pq - 1 : 3);
+                double al = 0.0, be = 0.0, ga = 0.0;
+                for (int k = 0; k < 4; ++k) {
+                    al += g[k][p] * g[k][p];
+                    be += g[k][q] * g[k][q];
+                    ga += g[k][p] * g[k][q];
+                }
+                if (ga * ga <= 1e-28 * (al * be)) continue;
+                rotated = true;
+                // tan of the rotation angle: t = sign(tau) 2 ga / (|tau| + sqrt(tau^2 + 4 ga^2)), tau = be - al
+                const double tau = be - al, g2 = 2.0 * ga;
+                const double h = sqrt_f64(tau * tau + g2 * g2);
+                const double t = g2 * rcp_f64((tau < 0.0) ? (tau - h) : (tau + h));
+                const double c = rsqrt_f64(1.0 + t * t), s = c * t;
+                for (int k = 0; k < 4; ++k) {
+                    const double gp = g[k][p], gq = g[k][q];
+                    g[k][p] = c * gp - s * gq;
+                    g[k][q] = s * gp + c * gq;
+                    const double vp = V[k][p], vq = V[k][q];
+                    V[k][p] = c * vp - s * vq;
+                    V[k][q] = s * vp + c * vq;
                 }
             }
             if (!rotated) break;
         }
         double best = 0.0;
         int arg = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
         for (int q = 0; q < 4; ++q) {
-            double nq = g[0][q] * g[0][q] + g[1][q] * g[1][q] + g[2][q] * g[2][q] + g[3][q] * g[3][q];
+            const double nq = g[0][q] * g[0][q] + g[1][q] * g[1][q] + g[2][q] * g[2][q] + g[3][q] * g[3][q];
             if (q == 0 || nq < best) { best = nq; arg = q; }
         }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int q = 0; q < 4; ++q)
-            if (q == arg) { x[0] = V[0][q]; x[1] = V[1][q]; x[2] = V[2][q]; x[3] = V[3][q]; }
+        x[0] = V[0][arg]; x[1] = V[1][arg]; x[2] = V[2][arg]; x[3] = V[3][arg];
     }
 
     // de-homogenised joint.  `path` (optional) reports which extractor produced it (tests).
@@ -354,7 +390,7 @@ struct DltAccum {
             return;
         }
         if (!invit(x)) { jacobi(x); how = 1; }
-        double ix = 1.0 / x[3];
+        double ix = rcp_f64(x[3]);
         X[0] = x[0] * ix; X[1] = x[1] * ix; X[2] = x[2] * ix;
         if (path) *path = how;
     }
@@ -367,28 +403,28 @@ struct DltAccum {
 // the transposed problem is solved, exactly as scipy does.  Returns 0, or -1 if infeasible.
 template <int MAXN, class CostFn>
 PAM_HD_NOINLINE int lsap_solve(int nr0, int nc0, CostFn cost, int* col4row_out) {
-    for (int i = 0; i < nr0; ++i) col4row_out[i] = -1;
+    PAM_NOUNROLL for (int i = 0; i < nr0; ++i) col4row_out[i] = -1;
     if (nr0 == 0 || nc0 == 0) return 0;
     const bool transpose = nc0 < nr0;
     const int nr = transpose ? nc0 : nr0, nc = transpose ? nr0 : nc0;
     double u[MAXN], v[MAXN], sp[MAXN];
     int path[MAXN], col4row[MAXN], row4col[MAXN], remaining[MAXN];
     uint64_t SR, SC;
-    for (int i = 0; i < nr; ++i) { u[i] = 0.0; col4row[i] = -1; }
-    for (int j = 0; j < nc; ++j) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
+    PAM_NOUNROLL for (int i = 0; i < nr; ++i) { u[i] = 0.0; col4row[i] = -1; }
+    PAM_NOUNROLL for (int j = 0; j < nc; ++j) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
     const double INF = HUGE_VAL;
-    for (int cur = 0; cur < nr; ++cur) {
+    PAM_NOUNROLL for (int cur = 0; cur < nr; ++cur) {
         double minVal = 0.0;
         int i = cur;
         int num_remaining = nc;
-        for (int it = 0; it < nc; ++it) { remaining[it] = nc - it - 1; sp[it] = INF; }
+        PAM_NOUNROLL for (int it = 0; it < nc; ++it) { remaining[it] = nc - it - 1; sp[it] = INF; }
         SR = 0ull; SC = 0ull;
         int sink = -1;
-        while (sink == -1) {
+        PAM_NOUNROLL while (sink == -1) {
             int index = -1;
             double lowest = INF;
             SR |= (1ull << i);
-            for (int it = 0; it < num_remaining; ++it) {
+            PAM_NOUNROLL for (int it = 0; it < num_remaining; ++it) {
                 int j = remaining[it];
                 double cij = transpose ? cost(j, i) : cost(i, j);
                 double r = minVal + cij - u[i] - v[j];
@@ -403,12 +439,12 @@ PAM_HD_NOINLINE int lsap_solve(int nr0, int nc0, CostFn cost, int* col4row_out) 
             remaining[index] = remaining[--num_remaining];
         }
         u[cur] += minVal;
-        for (int k = 0; k < nr; ++k)
+        PAM_NOUNROLL for (int k = 0; k < nr; ++k)
             if (((SR >> k) & 1ull) && k != cur) u[k] += minVal - sp[col4row[k]];
-        for (int j = 0; j < nc; ++j)
+        PAM_NOUNROLL for (int j = 0; j < nc; ++j)
             if ((SC >> j) & 1ull) v[j] -= minVal - sp[j];
         int j = sink;
-        while (true) {
+        PAM_NOUNROLL while (true) {
             int k = path[j];
             row4col[j] = k;
             int tmp = col4row[k]; col4row[k] = j; j = tmp;
@@ -416,10 +452,10 @@ PAM_HD_NOINLINE int lsap_solve(int nr0, int nc0, CostFn cost, int* col4row_out) 
         }
     }
     if (!transpose) {
-        for (int i = 0; i < nr; ++i) col4row_out[i] = col4row[i];
+        PAM_NOUNROLL for (int i = 0; i < nr; ++i) col4row_out[i] = col4row[i];
     } else {
         // col4row maps (original column) -> (original row)
-        for (int c = 0; c < nr; ++c) col4row_out[col4row[c]] = c;
+        PAM_NOUNROLL for (int c = 0; c < nr; ++c) col4row_out[col4row[c]] = c;
     }
     return 0;
 }

@@ -21,12 +21,18 @@ inline int make_devcfg(const pam_config& p, DevCfg& c, std::string& err) {
     if (p.stale_window < 0 || p.stale_window + 1 > PAM_MAX_AGEW) return bad("stale_window outside 0..7");
     if (!(p.sigma > 0.0) || !(p.arm_sigma > 0.0)) return bad("sigma / arm_sigma must be positive");
     c.V = p.num_cameras; c.J = p.num_joints; c.D = p.max_detections; c.max_trk = p.max_tracks;
+    c.max_hyp = p.num_cameras * p.max_detections < PAM_MAX_HYP ? p.num_cameras * p.max_detections : PAM_MAX_HYP;
     c.n_init = p.n_init; c.max_age = p.max_age; c.min_valid = p.min_valid_joints; c.stale_window = p.stale_window;
     c.arm_mask = p.arm_joint_mask;
     c.rad[0] = gaussian_weights(p.sigma, c.gw[0]);
     c.rad[1] = gaussian_weights(p.arm_sigma, c.gw[1]);
     if (c.rad[0] < 0 || c.rad[1] < 0) return bad("sigma too large: Gaussian radius int(4 sigma + .5) > 8");
     for (int T = 0; T < PAM_MAX_AGEW; ++T) c.w_age[T] = exp(-p.lambda_t * (double)T);
+    c.inv_joint_thr = 1.0 / p.joint_threshold;
+    for (int dt = 0; dt < 16; ++dt) {
+        c.inv_denom_tab[dt] = 1.0 / (p.alpha2d * (double)dt);
+        c.inv_decay_tab[dt] = 1.0 / exp(p.lambda_a * (double)dt);
+    }
     c.conf_thr = p.conf_threshold; c.epi_thr = p.epi_threshold; c.joint_thr = p.joint_threshold;
     c.alpha2d = p.alpha2d; c.lambda_a = p.lambda_a; c.veto_believe = p.veto_believe;
     c.fail_limit = (double)p.num_joints / 3.0;

@@ -53,14 +53,14 @@ __device__ __forceinline__ void stage_frame(float* sdst, int* scnt, const float*
                                             int V) {
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(sdst);
     if ((nfloats & 3) == 0 && ((uintptr_t)gsrc & 15) == 0) {
-        for (int i = threadIdx.x; i < nfloats / 4; i += blockDim.x)
+        PAM_NOUNROLL for (int i = threadIdx.x; i < nfloats / 4; i += blockDim.x)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + i * 16), "l"(gsrc + i * 4) : "memory");
     } else {
-        for (int i = threadIdx.x; i < nfloats; i += blockDim.x)
+        PAM_NOUNROLL for (int i = threadIdx.x; i < nfloats; i += blockDim.x)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbase + i * 4), "l"(gsrc + i) : "memory");
     }
     const unsigned cbase = (unsigned)__cvta_generic_to_shared(scnt);
-    for (int i = threadIdx.x; i < V; i += blockDim.x)
+    PAM_NOUNROLL for (int i = threadIdx.x; i < V; i += blockDim.x)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cbase + i * 4), "l"(gcnt + i) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -69,7 +69,7 @@ __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;"
 // dynamic shared memory of k_track_sequences: [arena doubles][2 x frame floats][2 x V counts]
 static inline size_t frame_floats_padded(const DevCfg& c) { return ((size_t)c.V * c.D * c.J * 3 + 3) / 4 * 4; }
 static inline size_t track_smem_bytes(const DevCfg& c) {
-    return (size_t)arena_doubles(c) * 8 + 2 * frame_floats_padded(c) * 4 + 2 * PAM_MAX_V * 4;
+    return (size_t)((arena_doubles(c) + 1) / 2 * 2) * 8 + 2 * frame_floats_padded(c) * 4 + 2 * PAM_MAX_V * 4;
 }
 
 struct TrackIO {
@@ -85,7 +85,8 @@ struct TrackIO {
 
 #define PAM_TRACK_THREADS_MAX 256
 
-__global__ void __launch_bounds__(PAM_TRACK_THREADS_MAX)
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, int T, int frame0, const TrackIO io) {
     extern __shared__ double arena[];
     __shared__ SeqShared sh;
@@ -95,12 +96,13 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
     g.bind(c, state + (int64_t)s * c.seq_bytes);
     const int nfl = c.V * c.D * c.J * 3;
     const int nfl_pad = (nfl + 3) / 4 * 4;
-    float* dbuf = (float*)(arena + arena_doubles(c));
+    float* dbuf = (float*)(arena + (arena_doubles(c) + 1) / 2 * 2);   // 16-byte aligned for cp.async
     int* cbuf = (int*)(dbuf + 2 * nfl_pad);
     const float* gd = io.dets + (int64_t)s * io.seq_frames * nfl;
     const int* gc = io.counts + (int64_t)s * io.seq_frames * c.V;
     if (T > 0) stage_frame(dbuf, cbuf, gd, gc, nfl, c.V);
     if (threadIdx.x == 0) carve(c, sh, arena);
+    __syncthreads();
     load_cameras(ctx, c, sh, cc);
     load_state(ctx, c, sh, g);
     stage_wait();
@@ -162,6 +164,7 @@ struct pam_handle {
     int device = 0;
     bool have_cameras = false;
     int track_threads = 128;
+    int track_minblocks = 4;
     DevBuf cam;              // packed camera constants
     CamConst cc{};
     // workspace of the *_host entry points
@@ -235,6 +238,8 @@ int pam_create(const pam_config* cfg, int device, pam_handle** out) {
         int want = cfg->max_tracks * cfg->num_joints;     // one thread per (track, joint)
         h->track_threads = want <= 64 ? 64 : (want <= 128 ? 128 : (want <= 192 ? 192 : 256));
     }
+    const char* mb = getenv("PAM_TRACK_MINBLOCKS");
+    if (mb) { int v = atoi(mb); if (v == 4 || v == 6 || v == 8) h->track_minblocks = v; }
     *out = h;
     return PAM_OK;
 }
@@ -286,14 +291,27 @@ int pam_track_reset(pam_handle* h, void* d_state, int32_t S, void* stream) {
     return PAM_OK;
 }
 
+typedef void (*track_kernel_t)(const DevCfg, const CamConst, char*, int, int, const TrackIO);
+
+// register budget variants: <= 128 threads with 4 / 6 / 8 CTAs per SM, or up to 256 threads
+static track_kernel_t pick_track_kernel(const pam_handle* h) {
+    if (h->track_threads > 128) return k_track_sequences<256, 2>;
+    switch (h->track_minblocks) {
+        case 8: return k_track_sequences<128, 8>;
+        case 6: return k_track_sequences<128, 6>;
+        default: return k_track_sequences<128, 4>;
+    }
+}
+
 static int launch_track(pam_handle* h, void* d_state, int32_t S, int32_t T, int32_t frame0, const TrackIO& io,
                         cudaStream_t stream) {
     const size_t smem = track_smem_bytes(h->dc);
+    track_kernel_t kern = pick_track_kernel(h);
     if (smem + sizeof(SeqShared) > 48 * 1024 && !h->smem_opt_in) {
-        CK(cudaFuncSetAttribute(k_track_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->smem_opt_in = true;
     }
-    k_track_sequences<<<S, h->track_threads, smem, stream>>>(h->dc, h->cc, (char*)d_state, T, frame0, io);
+    kern<<<S, h->track_threads, smem, stream>>>(h->dc, h->cc, (char*)d_state, T, frame0, io);
     h->launches += 1;
     CK(cudaGetLastError());
     return PAM_OK;

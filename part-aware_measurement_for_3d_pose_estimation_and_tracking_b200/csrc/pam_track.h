@@ -28,12 +28,15 @@ enum {
 
 // Launch-constant parameters (kernel argument, < 1 KB).
 struct DevCfg {
-    int V, J, D, max_trk;
+    int V, J, D, max_trk, max_hyp;
     int n_init, max_age, min_valid, stale_window;
     uint32_t arm_mask;
     int rad[2];                              // [0] sigma, [1] arm_sigma
     double gw[2][PAM_MAX_RADIUS + 1];
     double w_age[PAM_MAX_AGEW];              // exp(-lambda_t * T), T = 0..stale_window
+    double inv_joint_thr;
+    double inv_denom_tab[16];                // 1 / (alpha2d * dt), dt < 16
+    double inv_decay_tab[16];                // 1 / exp(lambda_a * dt)
     double conf_thr, epi_thr, joint_thr, alpha2d, lambda_a, veto_believe, fail_limit;
     float init_thr_f32;
     // per-sequence global state strides (bytes) -- see state_layout()
@@ -95,11 +98,16 @@ struct FrameOut {
 // Block-shared working set.  Fixed-size part; the J-dependent arrays live in `arena`.
 struct SeqShared {
     SeqHeader hdr;
-    TrkMeta trk[PAM_MAX_TRK];
-    double P[PAM_MAX_V][12];
-    double RK[PAM_MAX_V][9];
-    double pos[PAM_MAX_V][3];
-    double F[PAM_MAX_V][PAM_MAX_V][9];
+    TrkMeta* trk;     // [max_trk]            (arena)
+    double* P;        // [V][12]              (arena) camera constants widened to double
+    double* RK;       // [V][9]
+    double* pos;      // [V][3]
+    double* F;        // [V][V][9]
+    int Vn;           // = cfg.V (row stride of F)
+    PAM_HD const double* Pc(int cam) const { return P + cam * 12; }
+    PAM_HD const double* RKc(int cam) const { return RK + cam * 9; }
+    PAM_HD const double* posc(int cam) const { return pos + cam * 3; }
+    PAM_HD const double* Fc(int a, int b) const { return F + (a * Vn + b) * 9; }
     // frame scratch
     int n;                                   // tracks alive at frame start
     int m[PAM_MAX_V];                        // detections per camera
@@ -128,9 +136,9 @@ struct SeqShared {
     signed char hyp_det[PAM_MAX_HYP][PAM_MAX_V];
     unsigned char hyp_fail[PAM_MAX_HYP];
     signed char hyp_slot[PAM_MAX_HYP];
-    unsigned char hyp_veto[PAM_MAX_HYP][PAM_MAX_D];
-    unsigned char hyp_nvj[PAM_MAX_HYP][PAM_MAX_J];
-    double hyp_cost[PAM_MAX_HYP][PAM_MAX_D];
+    unsigned char* hyp_veto;   // [PAM_MAX_HYP][D]   (arena, aliases reproj)
+    unsigned char* hyp_nvj;    // [PAM_MAX_HYP][J]   (arena, aliases reproj)
+    double* hyp_cost;          // [PAM_MAX_HYP][D]   (arena, aliases reproj)
     // output
     int out_n;
     signed char out_slot[PAM_MAX_TRK];
@@ -145,20 +153,37 @@ struct SeqShared {
     double* hyp_pose; // [PAM_MAX_HYP][J][3]  (aliases reproj: phases do not overlap)
 };
 
+// Arena layout (doubles): [camera constants][track meta][aff][union{reproj | init scratch}][raw]
+PAM_HD int64_t arena_cam_doubles(const DevCfg& c) { return (int64_t)c.V * (12 + 9 + 3) + (int64_t)c.V * c.V * 9; }
+PAM_HD int64_t arena_meta_doubles(const DevCfg& c) { return ((int64_t)sizeof(TrkMeta) * c.max_trk + 7) / 8; }
+PAM_HD int64_t arena_init_doubles(const DevCfg& c) {
+    // hyp_pose + hyp_cost + (hyp_veto, hyp_nvj bytes)
+    return (int64_t)c.max_hyp * c.J * 3 + (int64_t)c.max_hyp * c.D + ((int64_t)c.max_hyp * (c.D + c.J) + 7) / 8;
+}
+PAM_HD int64_t arena_union_doubles(const DevCfg& c) {
+    int64_t r = (int64_t)c.V * c.max_trk * c.J * 2, h = arena_init_doubles(c);
+    return r > h ? r : h;
+}
 PAM_HD int64_t arena_doubles(const DevCfg& c) {
-    int64_t a = (int64_t)c.V * c.max_trk * c.D;
-    int64_t r = (int64_t)c.V * c.max_trk * c.J * 2;
-    int64_t h = (int64_t)PAM_MAX_HYP * c.J * 3;
-    int64_t w = (int64_t)c.max_trk * c.J * 3;
-    return a + (r > h ? r : h) + w;
+    return arena_cam_doubles(c) + arena_meta_doubles(c) + (int64_t)c.V * c.max_trk * c.D + arena_union_doubles(c) +
+           (int64_t)c.max_trk * c.J * 3;
 }
 PAM_HD void carve(const DevCfg& c, SeqShared& sh, double* arena) {
-    int64_t r = (int64_t)c.V * c.max_trk * c.J * 2;
-    int64_t h = (int64_t)PAM_MAX_HYP * c.J * 3;
-    sh.aff = arena;
-    sh.reproj = sh.aff + (int64_t)c.V * c.max_trk * c.D;
-    sh.hyp_pose = sh.reproj;
-    sh.raw = sh.reproj + (r > h ? r : h);
+    double* p = arena;
+    sh.Vn = c.V;
+    sh.P = p; p += (int64_t)c.V * 12;
+    sh.RK = p; p += (int64_t)c.V * 9;
+    sh.pos = p; p += (int64_t)c.V * 3;
+    sh.F = p; p += (int64_t)c.V * c.V * 9;
+    sh.trk = (TrkMeta*)p; p += arena_meta_doubles(c);
+    sh.aff = p; p += (int64_t)c.V * c.max_trk * c.D;
+    sh.reproj = p;
+    sh.hyp_pose = p;
+    sh.hyp_cost = p + (int64_t)c.max_hyp * c.J * 3;
+    sh.hyp_veto = (unsigned char*)(sh.hyp_cost + (int64_t)c.max_hyp * c.D);
+    sh.hyp_nvj = sh.hyp_veto + (int64_t)c.max_hyp * c.D;
+    p += arena_union_doubles(c);
+    sh.raw = p;
 }
 
 struct HostCtx {
@@ -182,7 +207,7 @@ struct HostCtx {
 #define PAM_MARK(k) do { } while (0)
 #endif
 
-#define PAM_FOR(i, N) for (int i = ctx.tid(), _n_##i = (N), _s_##i = ctx.nthreads(); i < _n_##i; i += _s_##i)
+#define PAM_FOR(i, N) PAM_NOUNROLL for (int i = ctx.tid(), _n_##i = (N), _s_##i = ctx.nthreads(); i < _n_##i; i += _s_##i)
 
 // camera constants: f32 in global memory (the reference's dtypes), widened once into shared.
 struct CamConst {
@@ -194,10 +219,10 @@ struct CamConst {
 
 template <class Ctx>
 PAM_HD void load_cameras(Ctx& ctx, const DevCfg& c, SeqShared& sh, const CamConst& cc) {
-    PAM_FOR(i, c.V * 12) sh.P[i / 12][i % 12] = (double)cc.P[i];
-    PAM_FOR(i, c.V * 9) sh.RK[i / 9][i % 9] = (double)cc.RKinv[i];
-    PAM_FOR(i, c.V * 3) sh.pos[i / 3][i % 3] = cc.pos[i];
-    PAM_FOR(i, c.V * c.V * 9) sh.F[i / (9 * c.V)][(i / 9) % c.V][i % 9] = (double)cc.F[i];
+    PAM_FOR(i, c.V * 12) sh.P[i] = (double)cc.P[i];
+    PAM_FOR(i, c.V * 9) sh.RK[i] = (double)cc.RKinv[i];
+    PAM_FOR(i, c.V * 3) sh.pos[i] = cc.pos[i];
+    PAM_FOR(i, c.V * c.V * 9) sh.F[i] = (double)cc.F[i];
 }
 
 template <class Ctx>
@@ -234,14 +259,14 @@ PAM_HD void dlt_from_views(const DevCfg& c, const SeqShared& sh, int Vt, const C
     int path = -1;
     if (fresh) {
         acc.reset(true);
-        for (int a = 0; a < Vt; ++a)
-            if ((alive >> a) & 1u) acc.add_view(sh.P[cid[a]], u[a], v[a], c.w_age[0]);
+        PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
+            if ((alive >> a) & 1u) acc.add_view(sh.Pc(cid[a]), u[a], v[a], c.w_age[0]);
         acc.solve(X, &path);
     }
     if (path < 0) {
         acc.reset(false);
-        for (int a = 0; a < Vt; ++a)
-            if ((alive >> a) & 1u) acc.add_view(sh.P[cid[a]], u[a], v[a], c.w_age[T ? T[a] : 0]);
+        PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
+            if ((alive >> a) & 1u) acc.add_view(sh.Pc(cid[a]), u[a], v[a], c.w_age[T ? T[a] : 0]);
         acc.solve(X, &path);
     }
 }
@@ -252,37 +277,36 @@ PAM_HD void dlt_from_views(const DevCfg& c, const SeqShared& sh, int Vt, const C
 PAM_HD int joint_update(const DevCfg& c, const SeqShared& sh, int Vt, const int* cid, const int* T,
                         const double* u, const double* v, const double* next, double* X) {
     uint32_t conflict[PAM_MAX_V];
-    for (int a = 0; a < Vt; ++a) conflict[a] = 0u;
+    PAM_NOUNROLL for (int a = 0; a < Vt; ++a) conflict[a] = 0u;
     bool any = false;
-    for (int a = 0; a < Vt; ++a)
-        for (int b = a + 1; b < Vt; ++b) {
-            double dab = epi_dist_f64(sh.F[cid[a]][cid[b]], u[a], v[a], u[b], v[b]);
-            double dba = epi_dist_f64(sh.F[cid[b]][cid[a]], u[b], v[b], u[a], v[a]);
+    PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
+        PAM_NOUNROLL for (int b = a + 1; b < Vt; ++b) {
+            double dab = epi_dist_f64(sh.Fc(cid[a], cid[b]), u[a], v[a], u[b], v[b]);
+            double dba = epi_dist_f64(sh.Fc(cid[b], cid[a]), u[b], v[b], u[a], v[a]);
             double D = (dab + dba) / 2.0;
-            double A = 1.0 - D / c.joint_thr;
+            double A = 1.0 - D * c.inv_joint_thr;
             if (A < 0.0) { conflict[a] |= (1u << b); any = true; }
         }
     uint32_t alive = (Vt >= 32) ? 0xffffffffu : ((1u << Vt) - 1u);
     if (any) {
         double rd[PAM_MAX_V];
-        for (int a = 0; a < Vt; ++a) rd[a] = 0.0;
-        for (int a = 0; a < Vt; ++a)
-            for (int b = a + 1; b < Vt; ++b) {
+        PAM_NOUNROLL for (int a = 0; a < Vt; ++a) rd[a] = 0.0;
+        PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
+            PAM_NOUNROLL for (int b = a + 1; b < Vt; ++b) {
                 if (!((conflict[a] >> b) & 1u)) continue;
                 if (!((alive >> a) & 1u) || !((alive >> b) & 1u)) continue;
-                if (rd[a] == 0.0) rd[a] = ray_point_distance(sh.RK[cid[a]], sh.pos[cid[a]], u[a], v[a], next);
-                if (rd[b] == 0.0) rd[b] = ray_point_distance(sh.RK[cid[b]], sh.pos[cid[b]], u[b], v[b], next);
+                if (rd[a] == 0.0) rd[a] = ray_point_distance(sh.RKc(cid[a]), sh.posc(cid[a]), u[a], v[a], next);
+                if (rd[b] == 0.0) rd[b] = ray_point_distance(sh.RKc(cid[b]), sh.posc(cid[b]), u[b], v[b], next);
                 if (rd[a] > rd[b]) alive &= ~(1u << a); else alive &= ~(1u << b);
             }
     }
-    int nv = 0;
-    for (int a = 0; a < Vt; ++a) nv += (alive >> a) & 1u;
+    const int nv = popcount32(alive);
     if (nv < 2) {
         X[0] = next[0]; X[1] = next[1]; X[2] = next[2];
         return nv;
     }
     bool fresh = true;
-    for (int a = 0; a < Vt; ++a)
+    PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
         if (((alive >> a) & 1u) && T[a] != 0) fresh = false;
     dlt_from_views(c, sh, Vt, cid, T, u, v, alive, fresh, X);
     return nv;
@@ -293,11 +317,11 @@ PAM_HD int joint_init(const DevCfg& c, const SeqShared& sh, int Vt, const signed
                       const double* u, const double* v, double* X) {
     float A[PAM_MAX_V][PAM_MAX_V];
     bool any = false;
-    for (int a = 0; a < Vt; ++a) {
+    PAM_NOUNROLL for (int a = 0; a < Vt; ++a) {
         A[a][a] = 1.0f - 0.0f / c.init_thr_f32;
-        for (int b = a + 1; b < Vt; ++b) {
+        PAM_NOUNROLL for (int b = a + 1; b < Vt; ++b) {
             double d1, d2;
-            epi_pair_cv(sh.F[cid[a]][cid[b]], u[a], v[a], u[b], v[b], d1, d2);
+            epi_pair_cv(sh.Fc(cid[a], cid[b]), u[a], v[a], u[b], v[b], d1, d2);
             float Df = (float)((d1 + d2) / 2.0);
             float Af = 1.0f - Df / c.init_thr_f32;
             A[a][b] = Af; A[b][a] = Af;
@@ -306,16 +330,15 @@ PAM_HD int joint_init(const DevCfg& c, const SeqShared& sh, int Vt, const signed
     }
     uint32_t alive = (1u << Vt) - 1u;
     if (any) {
-        for (int a = 0; a < Vt; ++a)
-            for (int b = a + 1; b < Vt; ++b) {
+        PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
+            PAM_NOUNROLL for (int b = a + 1; b < Vt; ++b) {
                 if (!(A[a][b] < 0.0f)) continue;
                 if (!((alive >> a) & 1u) || !((alive >> b) & 1u)) continue;
                 float s1 = np_sum(A[a], Vt), s2 = np_sum(A[b], Vt);
                 if (s1 > s2) alive &= ~(1u << b); else alive &= ~(1u << a);
             }
     }
-    int nv = 0;
-    for (int a = 0; a < Vt; ++a) nv += (alive >> a) & 1u;
+    const int nv = popcount32(alive);
     if (nv < 2) return nv;
     dlt_from_views(c, sh, Vt, cid, (const int*)nullptr, u, v, alive, true, X);
     return nv;
@@ -329,14 +352,14 @@ PAM_HD double hyp_cost(const DevCfg& c, const SeqShared& sh, const float* dets, 
     double total = 0.0;
     veto = false;
     const int nvw = sh.hyp_nviews[h];
-    for (int k = 0; k < nvw; ++k) {
+    PAM_NOUNROLL for (int k = 0; k < nvw; ++k) {
         const int c1 = sh.hyp_cam[h][k];
         const float* p = dets + ((int64_t)(c1 * c.D + sh.hyp_det[h][k]) * J) * 3;
         NpSumStream<double> acc;
         acc.begin(J);
-        for (int j = 0; j < J; ++j) {
+        PAM_NOUNROLL for (int j = 0; j < J; ++j) {
             double d1, d2v;
-            epi_pair_cv(sh.F[c1][c2], (double)p[j * 3 + 1], (double)p[j * 3 + 0], (double)o[j * 3 + 1],
+            epi_pair_cv(sh.Fc(c1, c2), (double)p[j * 3 + 1], (double)p[j * 3 + 0], (double)o[j * 3 + 1],
                         (double)o[j * 3 + 0], d1, d2v);
             acc.push((d1 * (double)p[j * 3 + 2] + d2v * (double)o[j * 3 + 2]) / 2.0);
         }
@@ -384,8 +407,13 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         const int dt = frame - t.hist_time[last];
         sh.last[i] = last;
         sh.dt[i] = dt;
-        sh.inv_denom[i] = 1.0 / (c.alpha2d * (double)dt);          // IterativeTracker.py:143
-        sh.inv_decay[i] = 1.0 / exp(c.lambda_a * (double)dt);      // IterativeTracker.py:148
+        if (dt >= 0 && dt < 16) {
+            sh.inv_denom[i] = c.inv_denom_tab[dt];                 // IterativeTracker.py:143
+            sh.inv_decay[i] = c.inv_decay_tab[dt];                 // IterativeTracker.py:148
+        } else {
+            sh.inv_denom[i] = 1.0 / (c.alpha2d * (double)dt);
+            sh.inv_decay[i] = 1.0 / exp(c.lambda_a * (double)dt);
+        }
         sh.fail[i] = 0;
     }
     PAM_FOR(cc, V) {
@@ -403,14 +431,14 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         const int last = (t.hist_start + t.hist_len - 1) % PAM_HIST;     // hist fields are stable here
         const double* X = g.hist + ((int64_t)(s * PAM_HIST + last) * J + j) * 3;
         const double x = X[0], y = X[1], z = X[2];
-        for (int cam = 0; cam < V; ++cam) {
+        PAM_NOUNROLL for (int cam = 0; cam < V; ++cam) {
             if (counts[cam] <= 0) continue;
-            const double* P = sh.P[cam];
+            const double* P = sh.Pc(cam);
             double a = P[0] * x + P[1] * y + P[2] * z + P[3];
             double b = P[4] * x + P[5] * y + P[6] * z + P[7];
             double w = P[8] * x + P[9] * y + P[10] * z + P[11];
             double* r = sh.reproj + ((int64_t)(cam * MT + i) * J + j) * 2;
-            const double iw = 1.0 / w;
+            const double iw = rcp_f64(w);
             r[0] = b * iw;   // v
             r[1] = a * iw;   // u
         }
@@ -427,10 +455,10 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         const double inv_denom = sh.inv_denom[i];
         double sum = 0.0;
         int cnt = 0;
-        for (int j = 0; j < J; ++j) {
+        PAM_NOUNROLL for (int j = 0; j < J; ++j) {
             double dv = r[j * 2 + 0] - (double)q[j * 3 + 0];
             double du = r[j * 2 + 1] - (double)q[j * 3 + 1];
-            double cj = 1.0 - sqrt(dv * dv + du * du) * inv_denom;
+            double cj = 1.0 - sqrt_f64(dv * dv + du * du) * inv_denom;
             if (cj > 0.0) { sum += cj; ++cnt; }
         }
         double a = (cnt > c.min_valid) ? sum / (double)cnt : 0.0;
@@ -451,11 +479,11 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         const int mm = sh.m[cam];
         const double* A = sh.aff + (int64_t)(cam * MT) * D;
         int cnt = 0, arg = -1;
-        for (int d = 0; d < mm; ++d)
+        PAM_NOUNROLL for (int d = 0; d < mm; ++d)
             if (A[i * D + d] > 0.0) { ++cnt; arg = d; }
         if (cnt == 1) {
             int col = 0;
-            for (int k = 0; k < n; ++k) col += (A[k * D + arg] > 0.0) ? 1 : 0;
+            PAM_NOUNROLL for (int k = 0; k < n; ++k) col += (A[k * D + arg] > 0.0) ? 1 : 0;
             if (col == 1) { sh.t2d[cam][i] = (signed char)arg; sh.d2t[cam][arg] = (signed char)i; }
             else sh.conflict[cam] = 1;
         } else if (cnt > 1) {
@@ -465,17 +493,17 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
     ctx.sync();
     {
         int any = 0;
-        for (int cam = 0; cam < V; ++cam) any |= sh.conflict[cam];
+        PAM_NOUNROLL for (int cam = 0; cam < V; ++cam) any |= sh.conflict[cam];
         if (any) {   // uniform
             PAM_FOR(cam, V) {
                 if (!sh.conflict[cam]) continue;
                 const int mm = sh.m[cam];
                 const double* A = sh.aff + (int64_t)cam * MT * D;
-                for (int i = 0; i < n; ++i) sh.t2d[cam][i] = -1;
-                for (int d = 0; d < D; ++d) sh.d2t[cam][d] = -1;
+                PAM_NOUNROLL for (int i = 0; i < n; ++i) sh.t2d[cam][i] = -1;
+                PAM_NOUNROLL for (int d = 0; d < D; ++d) sh.d2t[cam][d] = -1;
                 int col4row[PAM_MAX_TRK];
                 lsap_solve<PAM_MAX_TRK>(n, mm, [&](int i, int d) { return -A[i * D + d]; }, col4row);
-                for (int i = 0; i < n; ++i) {
+                PAM_NOUNROLL for (int i = 0; i < n; ++i) {
                     int d = col4row[i];
                     if (d >= 0 && A[i * D + d] > 0.0) { sh.t2d[cam][i] = (signed char)d; sh.d2t[cam][d] = (signed char)i; }
                 }
@@ -489,10 +517,10 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
     //      of every track (:310-325); mean confidence of every detection (calculate.py:8-14) ------
     PAM_FOR(i, n) {
         TrkMeta& t = sh.trk[sh.hdr.order[i]];
-        for (int cam = 0; cam < V; ++cam) {
+        PAM_NOUNROLL for (int cam = 0; cam < V; ++cam) {
             if (sh.t2d[cam][i] < 0) continue;
             int k = 0;
-            while (k < t.nviews && t.view_cid[k] != cam) ++k;
+            PAM_NOUNROLL while (k < t.nviews && t.view_cid[k] != cam) ++k;
             if (k == t.nviews) { t.nviews = k + 1; t.view_cid[k] = cam; }
             t.view_time[k] = frame;
             t.already = 1;
@@ -500,7 +528,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         }
         int cnt = 0;
         if (t.already)
-            for (int k = 0; k < t.nviews; ++k)
+            PAM_NOUNROLL for (int k = 0; k < t.nviews; ++k)
                 if (frame - t.view_time[k] <= c.stale_window) sh.gv_idx[i][cnt++] = (signed char)k;
         sh.gv_n[i] = cnt;
         sh.do_update[i] = (t.already && cnt >= 2) ? 1 : 0;
@@ -514,7 +542,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         const float* q = dets + (int64_t)(cam * D + d) * J3;
         double kept[PAM_MAX_J];
         int nk = 0;
-        for (int j = 0; j < J; ++j)
+        PAM_NOUNROLL for (int j = 0; j < J; ++j)
             if (q[j * 3 + 2] >= 0.0f) kept[nk++] = (double)q[j * 3 + 2];
         double b = np_sum(kept, nk) / (double)nk;   // 0/0 -> NaN like np.mean([])
         sh.believe[cam][d] = b;
@@ -538,7 +566,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         int cid[PAM_MAX_V], T[PAM_MAX_V];
         double u[PAM_MAX_V], v[PAM_MAX_V];
         const int Vt = sh.gv_n[i];
-        for (int a = 0; a < Vt; ++a) {
+        PAM_NOUNROLL for (int a = 0; a < Vt; ++a) {
             const int k = sh.gv_idx[i][a];
             const int cam = t.view_cid[k];
             cid[a] = cam;
@@ -559,18 +587,18 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
     {   // J3 consecutive floats per matched (camera, track) pair; lanes stride over the elements
         const int lanes = (ctx.nthreads() >= 32) ? 32 : ctx.nthreads();
         const int grp = ctx.tid() / lanes, ngrp = ctx.nthreads() / lanes, lane = ctx.tid() - grp * lanes;
-        for (int p = grp; p < V * n; p += ngrp) {
+        PAM_NOUNROLL for (int p = grp; p < V * n; p += ngrp) {
             const int cam = p / n, i = p - cam * n;
             const int d = sh.t2d[cam][i];
             if (d < 0) continue;
             float* dst = g.view + ((int64_t)(sh.hdr.order[i] * V + sh.vk[cam][i])) * J3;
             const float* src = dets + (int64_t)(cam * D + d) * J3;
-            for (int e = lane; e < J3; e += lanes) dst[e] = src[e];
+            PAM_NOUNROLL for (int e = lane; e < J3; e += lanes) dst[e] = src[e];
         }
     }
     PAM_FOR(cam, V) {
         int k = 0;
-        for (int d = 0; d < sh.m[cam]; ++d)
+        PAM_NOUNROLL for (int d = 0; d < sh.m[cam]; ++d)
             if (sh.um_flag[cam][d]) sh.um[cam][k++] = (signed char)d;
         sh.um_n[cam] = k;
     }
@@ -594,7 +622,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         const double* raw = sh.raw + (int64_t)(i * J + j) * 3;
         const double* hb = g.hist + ((int64_t)(s * PAM_HIST) * J + j) * 3;   // + ring * J3
         double o0 = raw[0] * w[0], o1 = raw[1] * w[0], o2 = raw[2] * w[0];
-        for (int k = rad; k >= 1; --k) {
+        PAM_NOUNROLL for (int k = rad; k >= 1; --k) {
             const int il = reflect_index(L - k, N), ir = reflect_index(L + k, N);
             const double* xl = (il == L) ? raw : hb + (int64_t)((start + il) % PAM_HIST) * J3;
             const double* xr = (ir == L) ? raw : hb + (int64_t)((start + ir) % PAM_HIST) * J3;
@@ -609,7 +637,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
             float h0 = (float)o0, h1 = (float)o1, h2 = (float)o2;    // newest entry = this frame's pose
             int cnt = 0;
-            for (int idx = len2 - 1; idx >= 1 && cnt < 5; --idx, ++cnt) {
+            PAM_NOUNROLL for (int idx = len2 - 1; idx >= 1 && cnt < 5; --idx, ++cnt) {
                 const double* lo = hb + (int64_t)((start2 + idx - 1) % PAM_HIST) * J3;
                 const float l0 = (float)lo[0], l1 = (float)lo[1], l2 = (float)lo[2];
                 a0 += h0 - l0; a1 += h1 - l1; a2 += h2 - l2;
@@ -625,7 +653,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         if (j == 0) t.hist_time[pos] = frame;     // no other thread reads this entry in this phase
         if (track_reported(c, sh, i)) {
             int k = 0;
-            for (int i2 = 0; i2 < i; ++i2) k += track_reported(c, sh, i2) ? 1 : 0;
+            PAM_NOUNROLL for (int i2 = 0; i2 < i; ++i2) k += track_reported(c, sh, i2) ? 1 : 0;
             if (out.joints) {
                 float* oj = out.joints + (int64_t)(k * J + j) * 3;
                 oj[0] = (float)o0; oj[1] = (float)o1; oj[2] = (float)o2;
@@ -640,7 +668,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
     //      decision whether new-track initialisation has anything to do ---------------------------
     if (ctx.tid() == 0) {
         int k = 0, wr = 0;
-        for (int i = 0; i < n; ++i) {
+        PAM_NOUNROLL for (int i = 0; i < n; ++i) {
             const int s = sh.hdr.order[i];
             TrkMeta& t = sh.trk[s];
             if (sh.do_update[i] && !((double)sh.fail[i] > c.fail_limit) && t.hist_len >= PAM_HIST)
@@ -669,12 +697,12 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         sh.hdr.frames_done += 1;
         if (out.count) *out.count = k;
         int cams_with = 0;
-        for (int cam = 0; cam < V; ++cam) cams_with += (sh.um_n[cam] > 0);
+        PAM_NOUNROLL for (int cam = 0; cam < V; ++cam) cams_with += (sh.um_n[cam] > 0);
         // a hypothesis needs views from two cameras to become a track (hypothesis.size() > 1)
         sh.do_init = (V >= 2 && cams_with >= 2) ? 1 : 0;
         sh.hyp_n = 0;
         if (sh.do_init) {
-            for (int q = 0; q < sh.um_n[0]; ++q) {
+            PAM_NOUNROLL for (int q = 0; q < sh.um_n[0]; ++q) {
                 sh.hyp_nviews[q] = 1; sh.hyp_cam[q][0] = 0; sh.hyp_det[q][0] = sh.um[0][q];
             }
             sh.hyp_n = sh.um_n[0];
@@ -686,27 +714,27 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
     // ---- phase 8: new-track initialisation (IterativeTracker.py:52-113); rare in steady state ---
     if (sh.do_init) {
         // grow hypotheses camera by camera
-        for (int cam = 1; cam < V; ++cam) {
+        PAM_NOUNROLL for (int cam = 1; cam < V; ++cam) {
             const int nh = sh.hyp_n, nd = sh.um_n[cam];
             if (nd == 0) continue;           // uniform
             PAM_FOR(it, nh * nd) {
                 const int h = it / nd, p = it % nd;
                 bool veto;
-                sh.hyp_cost[h][p] = hyp_cost(c, sh, dets, h, cam, sh.um[cam][p], veto);
-                sh.hyp_veto[h][p] = veto ? 1 : 0;
+                sh.hyp_cost[h * D + p] = hyp_cost(c, sh, dets, h, cam, sh.um[cam][p], veto);
+                sh.hyp_veto[h * D + p] = veto ? 1 : 0;
             }
             ctx.sync();
             if (ctx.tid() == 0) {
                 int col4row[PAM_MAX_HYP];
                 uint32_t handled = 0u;
-                lsap_solve<PAM_MAX_HYP>(nh, nd, [&](int h, int p) { return sh.hyp_cost[h][p]; }, col4row);
+                lsap_solve<PAM_MAX_HYP>(nh, nd, [&](int h, int p) { return sh.hyp_cost[h * D + p]; }, col4row);
                 int hn = nh;
-                for (int h = 0; h < nh; ++h) {
+                PAM_NOUNROLL for (int h = 0; h < nh; ++h) {
                     const int p = col4row[h];
                     if (p < 0) continue;
                     handled |= (1u << p);
-                    if (sh.hyp_veto[h][p]) {
-                        if (hn >= PAM_MAX_HYP) { sh.hdr.status = SEQ_ERR_HYP_OVERFLOW; break; }
+                    if (sh.hyp_veto[h * D + p]) {
+                        if (hn >= c.max_hyp) { sh.hdr.status = SEQ_ERR_HYP_OVERFLOW; break; }
                         sh.hyp_nviews[hn] = 1; sh.hyp_cam[hn][0] = (signed char)cam; sh.hyp_det[hn][0] = sh.um[cam][p];
                         ++hn;
                     } else {
@@ -714,9 +742,9 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
                         sh.hyp_cam[h][k] = (signed char)cam; sh.hyp_det[h][k] = sh.um[cam][p];
                     }
                 }
-                for (int p = 0; p < nd; ++p) {
+                PAM_NOUNROLL for (int p = 0; p < nd; ++p) {
                     if ((handled >> p) & 1u) continue;
-                    if (hn >= PAM_MAX_HYP) { sh.hdr.status = SEQ_ERR_HYP_OVERFLOW; break; }
+                    if (hn >= c.max_hyp) { sh.hdr.status = SEQ_ERR_HYP_OVERFLOW; break; }
                     sh.hyp_nviews[hn] = 1; sh.hyp_cam[hn][0] = (signed char)cam; sh.hyp_det[hn][0] = sh.um[cam][p];
                     ++hn;
                 }
@@ -733,14 +761,14 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             const int Vt = sh.hyp_nviews[h];
             if (Vt < 2) continue;
             double u[PAM_MAX_V], v[PAM_MAX_V];
-            for (int a = 0; a < Vt; ++a) {
+            PAM_NOUNROLL for (int a = 0; a < Vt; ++a) {
                 const float* q = dets + ((int64_t)(sh.hyp_cam[h][a] * D + sh.hyp_det[h][a]) * J + j) * 3;
                 v[a] = (double)q[0];
                 u[a] = (double)q[1];
             }
             double X[3] = {0.0, 0.0, 0.0};
             const int nv = joint_init(c, sh, Vt, sh.hyp_cam[h], u, v, X);
-            sh.hyp_nvj[h][j] = (unsigned char)nv;
+            sh.hyp_nvj[h * J + j] = (unsigned char)nv;
             if (nv < 2) sh.hyp_fail[h] = 1;     // benign race: every writer stores 1
             double* r = sh.hyp_pose + (int64_t)(h * J + j) * 3;
             r[0] = X[0]; r[1] = X[1]; r[2] = X[2];
@@ -748,11 +776,11 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         ctx.sync();
         // spawn tracks in hypothesis order (IterativeTracker.py:102-113)
         if (ctx.tid() == 0) {
-            for (int h = 0; h < nh; ++h) {
+            PAM_NOUNROLL for (int h = 0; h < nh; ++h) {
                 sh.hyp_slot[h] = -1;
                 if (sh.hyp_fail[h] || sh.hdr.status != SEQ_OK) continue;
                 int s = 0;
-                while (s < MT && ((sh.hdr.used_mask >> s) & 1u)) ++s;
+                PAM_NOUNROLL while (s < MT && ((sh.hdr.used_mask >> s) & 1u)) ++s;
                 if (s >= MT || sh.hdr.ntracks >= MT) { sh.hdr.status = SEQ_ERR_TRACK_OVERFLOW; continue; }
                 sh.hdr.used_mask |= (1u << s);
                 sh.hdr.order[sh.hdr.ntracks++] = s;
@@ -760,7 +788,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
                 t.track_id = sh.hdr.next_id++;
                 t.hits = 1; t.age = 1; t.tsu = 0; t.state = ST_TENTATIVE; t.already = 0;
                 t.nviews = sh.hyp_nviews[h];
-                for (int k = 0; k < t.nviews; ++k) { t.view_cid[k] = sh.hyp_cam[h][k]; t.view_time[k] = frame; }
+                PAM_NOUNROLL for (int k = 0; k < t.nviews; ++k) { t.view_cid[k] = sh.hyp_cam[h][k]; t.view_time[k] = frame; }
                 t.hist_start = 0; t.hist_len = 1; t.hist_time[0] = frame;
                 sh.hyp_slot[h] = (signed char)s;
             }
@@ -770,11 +798,11 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             const int h = it / J3, e = it % J3;
             const int s = sh.hyp_slot[h];
             if (s < 0) continue;
-            for (int k = 0; k < sh.hyp_nviews[h]; ++k)
+            PAM_NOUNROLL for (int k = 0; k < sh.hyp_nviews[h]; ++k)
                 g.view[(int64_t)(s * V + k) * J3 + e] = dets[(int64_t)(sh.hyp_cam[h][k] * D + sh.hyp_det[h][k]) * J3 + e];
             g.hist[(int64_t)(s * PAM_HIST) * J3 + e] = sh.hyp_pose[(int64_t)h * J3 + e];
             g.vel[(int64_t)s * J3 + e] = 0.0f;
-            if (e < J) g.nv[s * J + e] = sh.hyp_nvj[h][e];
+            if (e < J) g.nv[s * J + e] = sh.hyp_nvj[h * J + e];
         }
     }
     PAM_MARK(7);
