@@ -48,6 +48,9 @@
 
 namespace pam {
 
+// x / d for 0 <= x < 2^20 and small d, with inv = 1.0f / d: exact, 4 instructions instead of ~20
+PAM_HD int fast_div(int x, float inv) { return (int)(((float)x + 0.5f) * inv); }
+
 PAM_HD int popcount32(uint32_t x) {
 #if defined(__CUDA_ARCH__)
     return __popc(x);
@@ -465,10 +468,11 @@ PAM_HD_NOINLINE int lsap_solve(int nr0, int nc0, CostFn cost, int* col4row_out) 
 // ------------------------------------------------------------------------------------------
 // scipy 'reflect' (half-sample symmetric) extension: d c b a | a b c d | d c b a
 PAM_HD int reflect_index(int i, int n) {
-    int p = 2 * n;
-    i %= p;
-    if (i < 0) i += p;
-    return (i < n) ? i : (p - 1 - i);
+    PAM_NOUNROLL while (i < 0 || i >= n) {
+        if (i < 0) i = -1 - i;
+        if (i >= n) i = 2 * n - 1 - i;
+    }
+    return i;
 }
 
 // Gaussian weights of scipy.ndimage._gaussian_kernel1d, order 0: w[k] for |offset| = k.

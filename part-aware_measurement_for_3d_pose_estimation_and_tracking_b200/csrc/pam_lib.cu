@@ -110,19 +110,27 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
 #if defined(PAM_PHASE_TIMING)
     if (threadIdx.x == 0) { for (int k = 0; k < 24; ++k) sh.phase_cyc[k] = 0; sh.tlast = clock64(); }
 #endif
-    for (int t = 0; t < T; ++t) {
+    FrameOut o;
+    {
+        const int64_t f0 = (int64_t)s * io.seq_frames;
+        o.count = io.out_count ? io.out_count + f0 : nullptr;
+        o.ids = io.out_ids ? io.out_ids + f0 * c.max_trk : nullptr;
+        o.joints = io.out_joints ? io.out_joints + f0 * c.max_trk * c.J * 3 : nullptr;
+        o.nviews = io.out_nv ? io.out_nv + f0 * c.max_trk * c.J : nullptr;
+        o.assoc = io.out_assoc ? io.out_assoc + f0 * c.V * c.D : nullptr;
+    }
+    const int st_ids = c.max_trk, st_joints = c.max_trk * c.J * 3, st_nv = c.max_trk * c.J, st_assoc = c.V * c.D;
+    PAM_NOUNROLL for (int t = 0; t < T; ++t) {
         const int cur = t & 1;
         if (t + 1 < T)
             stage_frame(dbuf + (cur ^ 1) * nfl_pad, cbuf + (cur ^ 1) * PAM_MAX_V, gd + (int64_t)(t + 1) * nfl,
                         gc + (t + 1) * c.V, nfl, c.V);
-        const int64_t ft = (int64_t)s * io.seq_frames + t;
-        FrameOut o;
-        o.count = io.out_count ? io.out_count + ft : nullptr;
-        o.ids = io.out_ids ? io.out_ids + ft * c.max_trk : nullptr;
-        o.joints = io.out_joints ? io.out_joints + ft * c.max_trk * c.J * 3 : nullptr;
-        o.nviews = io.out_nv ? io.out_nv + ft * c.max_trk * c.J : nullptr;
-        o.assoc = io.out_assoc ? io.out_assoc + ft * c.V * c.D : nullptr;
         frame_step(ctx, c, sh, g, frame0 + t, dbuf + cur * nfl_pad, cbuf + cur * PAM_MAX_V, o);
+        if (o.count) o.count += 1;
+        if (o.ids) o.ids += st_ids;
+        if (o.joints) o.joints += st_joints;
+        if (o.nviews) o.nviews += st_nv;
+        if (o.assoc) o.assoc += st_assoc;
         stage_wait();
         __syncthreads();
         PAM_MARK(8);
@@ -164,7 +172,8 @@ struct pam_handle {
     int device = 0;
     bool have_cameras = false;
     int track_threads = 128;
-    int track_minblocks = 4;
+    int track_minblocks = 0;   // 0 = choose per launch
+    int num_sms = 148;
     DevBuf cam;              // packed camera constants
     CamConst cc{};
     // workspace of the *_host entry points
@@ -238,6 +247,7 @@ int pam_create(const pam_config* cfg, int device, pam_handle** out) {
         int want = cfg->max_tracks * cfg->num_joints;     // one thread per (track, joint)
         h->track_threads = want <= 64 ? 64 : (want <= 128 ? 128 : (want <= 192 ? 192 : 256));
     }
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     const char* mb = getenv("PAM_TRACK_MINBLOCKS");
     if (mb) { int v = atoi(mb); if (v == 4 || v == 6 || v == 8) h->track_minblocks = v; }
     *out = h;
@@ -294,9 +304,11 @@ int pam_track_reset(pam_handle* h, void* d_state, int32_t S, void* stream) {
 typedef void (*track_kernel_t)(const DevCfg, const CamConst, char*, int, int, const TrackIO);
 
 // register budget variants: <= 128 threads with 4 / 6 / 8 CTAs per SM, or up to 256 threads
-static track_kernel_t pick_track_kernel(const pam_handle* h) {
+static track_kernel_t pick_track_kernel(const pam_handle* h, int S) {
     if (h->track_threads > 128) return k_track_sequences<256, 2>;
-    switch (h->track_minblocks) {
+    // few sequences: latency matters, take the full register budget; many: 6 CTAs per SM hide latency
+    const int mb = h->track_minblocks ? h->track_minblocks : (S > 4 * h->num_sms ? 6 : 4);
+    switch (mb) {
         case 8: return k_track_sequences<128, 8>;
         case 6: return k_track_sequences<128, 6>;
         default: return k_track_sequences<128, 4>;
@@ -306,11 +318,9 @@ static track_kernel_t pick_track_kernel(const pam_handle* h) {
 static int launch_track(pam_handle* h, void* d_state, int32_t S, int32_t T, int32_t frame0, const TrackIO& io,
                         cudaStream_t stream) {
     const size_t smem = track_smem_bytes(h->dc);
-    track_kernel_t kern = pick_track_kernel(h);
-    if (smem + sizeof(SeqShared) > 48 * 1024 && !h->smem_opt_in) {
+    track_kernel_t kern = pick_track_kernel(h, S);
+    if (smem + sizeof(SeqShared) > 48 * 1024)
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        h->smem_opt_in = true;
-    }
     kern<<<S, h->track_threads, smem, stream>>>(h->dc, h->cc, (char*)d_state, T, frame0, io);
     h->launches += 1;
     CK(cudaGetLastError());

@@ -29,6 +29,7 @@ enum {
 // Launch-constant parameters (kernel argument, < 1 KB).
 struct DevCfg {
     int V, J, D, max_trk, max_hyp;
+    float inv_J, inv_D, inv_V, inv_VD;       // reciprocals for fast_div
     int n_init, max_age, min_valid, stale_window;
     uint32_t arm_mask;
     int rad[2];                              // [0] sigma, [1] arm_sigma
@@ -422,10 +423,10 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         sh.m[cc] = mm;
         sh.conflict[cc] = 0;
     }
-    PAM_FOR(i, V * MT) sh.t2d[i / MT][i % MT] = -1;
-    PAM_FOR(i, V * D) sh.d2t[i / D][i % D] = -1;
+    PAM_FOR(i, PAM_MAX_V * PAM_MAX_TRK / 4) ((int*)sh.t2d)[i] = -1;
+    PAM_FOR(i, PAM_MAX_V * PAM_MAX_D / 4) ((int*)sh.d2t)[i] = -1;
     PAM_FOR(it, n * J) {
-        const int i = it / J, j = it - i * J;
+        const int i = fast_div(it, c.inv_J), j = it - i * J;
         const int s = sh.hdr.order[i];
         const TrkMeta& t = sh.trk[s];
         const int last = (t.hist_start + t.hist_len - 1) % PAM_HIST;     // hist fields are stable here
@@ -448,7 +449,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
 
     // ---- phase 2: track x detection affinity (IterativeTracker.py:139-149) ----------------------
     PAM_FOR(it, V * n * D) {
-        const int cam = it / (n * D), rem = it - cam * (n * D), i = rem / D, d = rem - i * D;
+        const int i = fast_div(it, c.inv_VD), rem = it - i * (V * D), cam = fast_div(rem, c.inv_D), d = rem - cam * D;
         if (d >= sh.m[cam]) continue;
         const double* r = sh.reproj + (int64_t)(cam * MT + i) * J * 2;
         const float* q = dets + (int64_t)(cam * D + d) * J3;
@@ -461,7 +462,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             double cj = 1.0 - sqrt_f64(dv * dv + du * du) * inv_denom;
             if (cj > 0.0) { sum += cj; ++cnt; }
         }
-        double a = (cnt > c.min_valid) ? sum / (double)cnt : 0.0;
+        double a = (cnt > c.min_valid) ? sum * rcp_f64((double)cnt) : 0.0;
         a = a * sh.inv_decay[i];
         if (a != a) a = 0.0;
         sh.aff[(int64_t)(cam * MT + i) * D + d] = a;
@@ -475,7 +476,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
     // contains exactly those pairs, so they are taken directly; otherwise the camera is flagged
     // and solved with the full shortest-augmenting-path algorithm below.
     PAM_FOR(it, V * n) {
-        const int cam = it / n, i = it % n;
+        const int i = fast_div(it, c.inv_V), cam = it - i * V;
         const int mm = sh.m[cam];
         const double* A = sh.aff + (int64_t)(cam * MT) * D;
         int cnt = 0, arg = -1;
@@ -534,7 +535,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         sh.do_update[i] = (t.already && cnt >= 2) ? 1 : 0;
     }
     PAM_FOR(it, V * D) {
-        const int cam = it / D, d = it % D;
+        const int cam = fast_div(it, c.inv_D), d = it - cam * D;
         sh.um_flag[cam][d] = 0;
         const int i = (d < sh.m[cam]) ? sh.d2t[cam][d] : -1;
         if (out.assoc) out.assoc[it] = (i >= 0) ? sh.trk[sh.hdr.order[i]].track_id : -1;
@@ -554,7 +555,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
     // ---- phase 5: per (track, joint): part-aware view filter + DLT (IterativeTracker.py:337-369);
     //      persist the matched detections as the tracks' newest views; unmatched lists ---------
     PAM_FOR(it, n * J) {
-        const int i = it / J, j = it - i * J;
+        const int i = fast_div(it, c.inv_J), j = it - i * J;
         if (!sh.do_update[i]) continue;
         const int s = sh.hdr.order[i];
         const TrkMeta& t = sh.trk[s];
@@ -588,7 +589,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         const int lanes = (ctx.nthreads() >= 32) ? 32 : ctx.nthreads();
         const int grp = ctx.tid() / lanes, ngrp = ctx.nthreads() / lanes, lane = ctx.tid() - grp * lanes;
         PAM_NOUNROLL for (int p = grp; p < V * n; p += ngrp) {
-            const int cam = p / n, i = p - cam * n;
+            const int i = fast_div(p, c.inv_V), cam = p - i * V;
             const int d = sh.t2d[cam][i];
             if (d < 0) continue;
             float* dst = g.view + ((int64_t)(sh.hdr.order[i] * V + sh.vk[cam][i])) * J3;
@@ -609,7 +610,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
     //      sample (IterativeTracker.py:371-383), history append, velocity = float32 mean of the
     //      last <= 5 differences (:385-395), output row (ivclabpose.py:265-287) ------------------
     PAM_FOR(it, n * J) {
-        const int i = it / J, j = it - i * J;
+        const int i = fast_div(it, c.inv_J), j = it - i * J;
         if (!track_ok(c, sh, i)) continue;
         const int s = sh.hdr.order[i];
         TrkMeta& t = sh.trk[s];

@@ -18,8 +18,9 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(io.StringIO(out)))
 kname = rows[0][1]; hdr = rows[1]
 ia, iex = hdr.index("Address"), hdr.index("Instructions Executed")
-kbase = re.match(r"(\w+)", kname).group(1)
-kfunc = [f for f in sorted({f for f, _ in addr2line}) if kbase in f][0]
+kbase = re.match(r"(\w+)", kname.replace("void ", "")).group(1)
+cands = [f for f in sorted({f for f, _ in addr2line}) if kbase in f]
+kfunc = ([f for f in cands if os.environ.get("KVARIANT", "ILi128ELi4") in f] or cands)[0]
 base = None
 hot = collections.Counter(); ops = collections.Counter()
 for r in rows[2:]:
