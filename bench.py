@@ -286,8 +286,15 @@ def main():
     n_out = reports / float(S * T)
     b_frame = 4.0 * (3 * V * D * J + 3 * n_out * J + n_out)
     achieved = b_frame * S * T / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:   # measured DRAM bytes per frame of this kernel (ncu --set full, profiles/), scaled to one launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if a.shape == "shelf":
+            traffic = tj["dram_bytes_per_frame"] * S * T
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "traffic": traffic, "algorithmic_bytes": b_frame * S * T, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "kernel": "k_track_sequences", "kernel_ms": kernel_ms, "bytes_per_frame": b_frame,
                 "note": "frame-serial FP64 state machine: latency/FP64-issue bound, not HBM bound"}
 
