@@ -124,18 +124,22 @@ __global__ void k_epipolar_pairs(const float* __restrict__ F, int V, const doubl
 }
 
 // ---- a7: all-pairs form with float32 stores (dense crowd) ------------------------------------------
-// One CTA = a TILE x TILE block of detection pairs; both pose tiles are staged in shared memory as
-// (u, v) pairs; each thread walks the joints of its pairs.  aff [M][M] f32 (25 between detections
-// of one camera, 0 on the diagonal), D [M][M][J] f32 or null.
+// One CTA = a TILE x TILE block of detection pairs (upper-triangular tiles only; results are
+// mirrored).  Both pose tiles are staged in shared memory as (u, v) pairs; each thread walks the
+// joints of its pairs in FP64.  aff [M][M] f32 (25 between detections of one camera, 0 on the
+// diagonal).  The optional per-joint tensor D [M][M][J] f32 (299 MB at M = 1984) is staged per tile
+// in shared memory and written out as contiguous TILE*J-float runs in BOTH orientations, so the
+// mirrored half is coalesced too.
 #define PAM_AP_TILE 32
 __global__ void __launch_bounds__(256)
 k_epipolar_allpairs(const float* __restrict__ F, int V, const double* __restrict__ pose, const int* __restrict__ cam,
                     int M, int J, float* __restrict__ aff, float* __restrict__ D) {
-    extern __shared__ double tile[];           // [2][TILE][J][2]
+    extern __shared__ double tile[];           // [2][TILE][J][2] doubles, then (if D) [TILE][TILE][J] floats
     const int ti = blockIdx.y, tj = blockIdx.x;
-    if (tj < ti) return;                       // upper-triangular tiles only; results are mirrored
+    if (tj < ti) return;
     double* A = tile;
     double* Bt = tile + PAM_AP_TILE * J * 2;
+    float* Ds = (float*)(tile + 2 * PAM_AP_TILE * J * 2);
     for (int e = threadIdx.x; e < PAM_AP_TILE * J; e += blockDim.x) {
         const int r = e / J, j = e - r * J;
         const int ia = ti * PAM_AP_TILE + r, ib = tj * PAM_AP_TILE + r;
@@ -146,16 +150,16 @@ k_epipolar_allpairs(const float* __restrict__ F, int V, const double* __restrict
     for (int p = threadIdx.x; p < PAM_AP_TILE * PAM_AP_TILE; p += blockDim.x) {
         const int r = p / PAM_AP_TILE, cidx = p - r * PAM_AP_TILE;
         const int i = ti * PAM_AP_TILE + r, j2 = tj * PAM_AP_TILE + cidx;
-        if (i >= M || j2 >= M || j2 < i) continue;
-        if (i == j2) {
-            aff[(int64_t)i * M + i] = 0.0f;
-            if (D) for (int j = 0; j < J; ++j) D[((int64_t)i * M + i) * J + j] = 0.0f;
-            continue;
-        }
+        float* ds = D ? Ds + (int64_t)p * J : nullptr;
+        if (i >= M || j2 >= M) continue;
         const int ci = cam[i], cj = cam[j2];
-        if (ci == cj) {
-            aff[(int64_t)i * M + j2] = 25.0f; aff[(int64_t)j2 * M + i] = 25.0f;
-            if (D) for (int j = 0; j < J; ++j) { D[((int64_t)i * M + j2) * J + j] = 0.0f; D[((int64_t)j2 * M + i) * J + j] = 0.0f; }
+        if (i == j2 || ci == cj || (ti == tj && j2 < i)) {
+            // diagonal: 0; same camera: 25 / zeros (matching.py:97-102); lower half of a diagonal tile:
+            // filled by its mirror below
+            if (i == j2) aff[(int64_t)i * M + i] = 0.0f;
+            else if (ci == cj) aff[(int64_t)i * M + j2] = 25.0f;
+            if (ds && !(ti == tj && j2 < i && ci != cj)) for (int j = 0; j < J; ++j) ds[j] = 0.0f;
+            if (ci == cj && i != j2 && ti != tj) aff[(int64_t)j2 * M + i] = 25.0f;
             continue;
         }
         double Fm[9];
@@ -169,11 +173,34 @@ k_epipolar_allpairs(const float* __restrict__ F, int V, const double* __restrict
             epi_pair_cv(Fm, xa[j * 2], xa[j * 2 + 1], xb[j * 2], xb[j * 2 + 1], d1, d2);
             const double sym = (d1 + d2) / 2.0;
             acc.push(sym);
-            if (D) { D[((int64_t)i * M + j2) * J + j] = (float)sym; D[((int64_t)j2 * M + i) * J + j] = (float)sym; }
+            if (ds) ds[j] = (float)sym;
         }
         const float m = (float)(acc.total() / (double)J);
         aff[(int64_t)i * M + j2] = m;
         aff[(int64_t)j2 * M + i] = m;
+        if (ds && ti == tj) {                  // mirror inside a diagonal tile
+            float* dm = Ds + (int64_t)(cidx * PAM_AP_TILE + r) * J;
+            for (int j = 0; j < J; ++j) dm[j] = ds[j];
+        }
+    }
+    if (!D) return;
+    __syncthreads();
+    // row i of the tile = TILE*J contiguous floats of D[i][tj*TILE ...]; and, for off-diagonal tiles,
+    // column c of the tile = TILE*J contiguous floats of D[j2][ti*TILE ...]
+    const int run = PAM_AP_TILE * J;
+    const int cols = min(PAM_AP_TILE, M - tj * PAM_AP_TILE), rows = min(PAM_AP_TILE, M - ti * PAM_AP_TILE);
+    for (int e = threadIdx.x; e < PAM_AP_TILE * run; e += blockDim.x) {
+        const int r = e / run, k = e - r * run;          // k = cidx * J + j
+        if (r < rows && k < cols * J)
+            D[((int64_t)(ti * PAM_AP_TILE + r) * M + tj * PAM_AP_TILE) * J + k] = Ds[(int64_t)r * run + k];
+    }
+    if (ti != tj) {
+        for (int e = threadIdx.x; e < PAM_AP_TILE * run; e += blockDim.x) {
+            const int cidx = e / run, k = e - cidx * run;   // k = r * J + j
+            const int r = k / J, j = k - r * J;
+            if (cidx < cols && r < rows)
+                D[((int64_t)(tj * PAM_AP_TILE + cidx) * M + ti * PAM_AP_TILE) * J + k] = Ds[(int64_t)(r * PAM_AP_TILE + cidx) * J + j];
+        }
     }
 }
 
@@ -222,30 +249,63 @@ __global__ void k_view_filter(const float* __restrict__ RKinv, const double* __r
 // ---- a10 / a11: weighted DLT of B x J joints over Vt views -------------------------------------------
 // pose [B][Vt][J][3] (v,u,conf), cam [B][Vt], w [B][Vt] = exp(-lambda_t T), keep [B][J][Vt] or null,
 // next [B][J][3] or null (used when < 2 views survive; NaN if null)  ->  out [B][J][3]
+// LANES threads cooperate on one joint: with all-fresh views the Gram matrix is additive, so each lane
+// folds every LANES-th view and the 10 entries are summed with warp shuffles (dense rigs: 31 views);
+// systems with stale views (weights < 1) are folded with Givens rotations by the first lane.
+template <int LANES>
 __global__ void k_triangulate(const float* __restrict__ P, const double* __restrict__ pose, const int* __restrict__ cam,
                               const double* __restrict__ w, const unsigned char* __restrict__ keep,
                               const double* __restrict__ next, int B, int Vt, int J, double* __restrict__ out) {
-    const int it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= B * J) return;
-    const int b = it / J, j = it - b * J;
-    const unsigned char* kp = keep ? keep + (int64_t)it * Vt : nullptr;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int it = gt / LANES, lane = gt % LANES;
+    const bool active = it < B * J;
+    const int b = active ? it / J : 0, j = active ? it - b * J : 0;
+    const unsigned char* kp = (keep && active) ? keep + (int64_t)it * Vt : nullptr;
     int nv = 0;
     bool fresh = true;
-    for (int a = 0; a < Vt; ++a) {
-        if (kp && !kp[a]) continue;
-        ++nv;
-        if (w[(int64_t)b * Vt + a] != 1.0) fresh = false;
-    }
+    if (active)
+        for (int a = 0; a < Vt; ++a) {
+            if (kp && !kp[a]) continue;
+            ++nv;
+            if (w[(int64_t)b * Vt + a] != 1.0) fresh = false;
+        }
     double* o = out + (int64_t)it * 3;
-    if (nv < 2) {
+    if (active && nv < 2 && lane == 0) {
         if (next) { o[0] = next[(int64_t)it * 3]; o[1] = next[(int64_t)it * 3 + 1]; o[2] = next[(int64_t)it * 3 + 2]; }
         else { o[0] = o[1] = o[2] = nan(""); }
-        return;
     }
+    const bool work = active && nv >= 2;
     DltAccum acc;
     int path = -1;
-    for (int pass = fresh ? 0 : 1; pass < 2 && path < 0; ++pass) {
-        acc.reset(pass == 0);
+    if (fresh) {
+        acc.reset(true);
+        if (work)
+            for (int a = lane; a < Vt; a += LANES) {
+                if (kp && !kp[a]) continue;
+                double Pm[12];
+                load12(P + cam[(int64_t)b * Vt + a] * 12, Pm);
+                const double* q = pose + (((int64_t)b * Vt + a) * J + j) * 3;
+                acc.add_view(Pm, q[1], q[0], 1.0);
+            }
+        if (LANES > 1) {
+#pragma unroll
+            for (int off = LANES / 2; off > 0; off >>= 1) {
+                acc.r00 += __shfl_down_sync(0xffffffffu, acc.r00, off, LANES);
+                acc.r01 += __shfl_down_sync(0xffffffffu, acc.r01, off, LANES);
+                acc.r02 += __shfl_down_sync(0xffffffffu, acc.r02, off, LANES);
+                acc.r03 += __shfl_down_sync(0xffffffffu, acc.r03, off, LANES);
+                acc.r11 += __shfl_down_sync(0xffffffffu, acc.r11, off, LANES);
+                acc.r12 += __shfl_down_sync(0xffffffffu, acc.r12, off, LANES);
+                acc.r13 += __shfl_down_sync(0xffffffffu, acc.r13, off, LANES);
+                acc.r22 += __shfl_down_sync(0xffffffffu, acc.r22, off, LANES);
+                acc.r23 += __shfl_down_sync(0xffffffffu, acc.r23, off, LANES);
+                acc.r33 += __shfl_down_sync(0xffffffffu, acc.r33, off, LANES);
+            }
+        }
+        if (work && lane == 0) acc.solve(o, &path);
+    }
+    if (work && lane == 0 && path < 0) {
+        acc.reset(false);
         for (int a = 0; a < Vt; ++a) {
             if (kp && !kp[a]) continue;
             double Pm[12];

@@ -47,15 +47,23 @@ for c in range(V):
     for d in range(st.counts[1, c]):
         pm[st.person_of_det[1, c, d], c] = st.dets[1, c, d]
 d_pm = torch.from_numpy(pm).cuda()
-camv = np.tile(np.arange(V), (P, 1))
-w = np.ones((P, V))
-ms = timeit(lambda: o.triangulate(camv, d_pm, w, as_numpy=False))
+d_camv = torch.from_numpy(np.tile(np.arange(V), (P, 1)).astype(np.int32)).cuda()
+d_w = torch.ones((P, V), dtype=torch.float64, device="cuda")
+d_X = torch.empty((P, J, 3), dtype=torch.float64, device="cuda")
+def tri():
+    o._call(o.lib.pam_triangulate, o._p(d_pm), o._p(d_camv), o._p(d_w), None, None, P, V, o._p(d_X), o._stream())
+ms = timeit(tri)
 rows.append(("pam_triangulate (64 people x 19 joints x 31 views)", ms, P * V * J * 3 * 8 + P * J * 3 * 8, P * J * (V * 2 * 30 + 400)))
 # association affinity: 64 tracks x 64 detections x 31 cameras
 tracks = st.gt[0]
 dets = st.frame_detections(1)
-ms = timeit(lambda: o.assoc_affinity(tracks, np.ones(P, int), dets, as_numpy=False))
-rows.append(("pam_assoc_affinity (31 x 64 x 64) incl. host packing", ms, V * P * J * 3 * 8 + 8 * V * P * P, V * P * P * J * 30))
+d_tr = torch.from_numpy(tracks).cuda(); d_dt = torch.ones(P, dtype=torch.int32, device="cuda")
+d_dets = torch.from_numpy(np.stack([np.asarray(d) for d in dets])).cuda(); d_cnt = torch.full((V,), P, dtype=torch.int32, device="cuda")
+d_aff = torch.empty((V, P, P), dtype=torch.float64, device="cuda")
+def assoc():
+    o._call(o.lib.pam_assoc_affinity, o._p(d_tr), o._p(d_dt), o._p(d_dets), o._p(d_cnt), P, P, o._p(d_aff), o._stream())
+ms = timeit(assoc)
+rows.append(("pam_assoc_affinity (31 cameras x 64 tracks x 64 detections)", ms, V * P * J * 3 * 8 + 8 * V * P * P, V * P * P * J * 30))
 aff, counts = o.assoc_affinity(tracks, np.ones(P, int), dets, as_numpy=False)
 cost = (-aff).contiguous()
 out = torch.empty((V, P), dtype=torch.int32, device="cuda")
