@@ -58,7 +58,7 @@ def parse():
 # ----------------------------------------------------------------------------------------------
 # data
 # ----------------------------------------------------------------------------------------------
-def generate(shape, seq_ids, T, dets_out, counts_out, workers=None):
+def generate(shape, seq_ids, T, dets_out, counts_out, gt_out=None, workers=None):
     from concurrent.futures import ThreadPoolExecutor
     import pam_b200  # noqa: F401
     from pam_b200 import synth
@@ -68,6 +68,8 @@ def generate(shape, seq_ids, T, dets_out, counts_out, workers=None):
         st = synth.make_stream(shape, seq_ids[k], T, rig=rig)
         dets_out[k] = st.dets
         counts_out[k] = st.counts
+        if gt_out is not None:
+            gt_out[k] = st.gt
 
     with ThreadPoolExecutor(workers or min(32, os.cpu_count() or 8)) as ex:
         list(ex.map(one, range(len(seq_ids))))
@@ -200,8 +202,10 @@ def main():
     h_dets = torch.empty((S, T, V, D, J, 3), dtype=torch.float32, pin_memory=True)
     h_counts = torch.empty((S, T, V), dtype=torch.int32, pin_memory=True)
     seq_ids = [rank * S + s for s in range(S)]          # distinct seeds on every rank
+    do_eval = (J == 14)                                 # PCP counters need the 14 Shelf/Campus joints
+    h_gt = np.empty((S, T, sh.P, J, 3), np.float64) if do_eval else None
     t0 = time.time()
-    rig = generate(a.shape, seq_ids, T, h_dets.numpy(), h_counts.numpy())
+    rig = generate(a.shape, seq_ids, T, h_dets.numpy(), h_counts.numpy(), h_gt)
     gen_s = time.time() - t0
     cams = camera.GetCameraParameters(rig)
     trk = tracker.SequenceTracker(cams, synth.tracker_params(a.shape), S, max_detections=D, max_tracks=MT,
@@ -209,8 +213,14 @@ def main():
     d_dets = h_dets.to(dev, non_blocking=True)
     d_counts = h_counts.to(dev, non_blocking=True)
     out = trk.alloc_outputs(T, nviews=False, assoc=False)
-    counters = torch.zeros(4, dtype=torch.int64, device=dev)
+    # run counters, summed over ranks -- the only collective of the path: [reports, frames,
+    # PCP correct, PCP evaluated, MPJPE sum (um), joints counted]
+    counters = torch.zeros(6, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream(dev)
+    from pam_b200 import evaluate
+    d_gt = torch.from_numpy(h_gt).to(dev) if do_eval else None
+    pcp = torch.zeros((sh.P, 10, 2), dtype=torch.int64, device=dev)
+    mpj = torch.zeros(2, dtype=torch.float64, device=dev)
 
     def step(timed_events=None):
         trk.restart()                                    # empty trackers: every step does the same work
@@ -219,9 +229,15 @@ def main():
         trk.run(d_dets, d_counts, out=out, frame0=0)
         if timed_events is not None:
             timed_events[1].record(stream)
-        # run counters (reports, frames); summed over ranks -- the only collective of the path
         counters[0] = out["count"].sum()
         counters[1] = S * T
+        if do_eval:                                      # PCP / MPJPE counters on device (evalmodel.py:120-206)
+            pcp.zero_(); mpj.zero_()
+            evaluate.pcp_counters(trk, out, d_gt, counters=pcp, mpjpe=mpj, frame_begin=3)
+            counters[2] = pcp[:, :, 0].sum()
+            counters[3] = pcp[:, :, 1].sum()
+            counters[4] = (mpj[0] * 1e6).to(torch.int64)
+            counters[5] = mpj[1].to(torch.int64)
         pdist.reduce_counters(counters)
 
     for _ in range(a.warmup):
@@ -243,7 +259,7 @@ def main():
     pdist.barrier()
     elapsed_ms = pdist.max_over_ranks(e0.elapsed_time(e1), dev)
     clocks = sampler.summary()
-    launches = trk.launches - launches0
+    launches = trk.launches - launches0              # tracker + evaluator kernels of this handle
     trk.check()
     kernel_ms = float(np.mean([x.elapsed_time(y) for x, y in kev]))
     reports = int(out["count"].sum().item())
@@ -313,6 +329,8 @@ def main():
                                f"sequences per GPU", "sequences_per_gpu": S, "frames": T, "max_tracks": MT,
                    "l2": f"inputs larger than L2 ({d_dets.numel() * 4 / 1e9:.2f} GB of detections per GPU per step)",
                    "gen_seconds": round(gen_s, 1), "reports_per_step": int(counters[0].item()),
+                   "pcp_percent": (round(100.0 * counters[2].item() / max(1, counters[3].item()), 3) if do_eval else None),
+                   "mpjpe_mm": (round(counters[4].item() / max(1, counters[5].item()) / 1e3, 3) if do_eval else None),
                    "threads_per_cta": int(os.environ.get("PAM_TRACK_THREADS", "0")) or "auto"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
     }

@@ -192,6 +192,17 @@ int pam_triangulate(pam_handle* h, const double* d_pose, const int32_t* d_cam, c
 int pam_ray_distance(pam_handle* h, int32_t camera, const double* d_uv, const double* d_points3d_or_null, int32_t n,
                      double* d_dist_or_null, double* d_dirs_or_null, void* stream);
 
+/* PCP / MPJPE counters of Evaluate3DPose_PCP (evalmodel.py:120-206, eval/transformation.py:5-39,
+ * eval/numeric.py:5-25) straight from the tracker's output tensors: d_out_count [S][T], d_out_joints
+ * [S][T][max_tracks][J][3] f32; d_gt [S][T][P][14][3] f64 (Shelf/Campus joint order), d_gt_valid
+ * [S][T][P] u8; frames frame_begin <= t < frame_end; alpha = 0.5 in the reference.  Accumulates (does
+ * not reset) d_counters [P][10][2] u64 = (correct, evaluated) per actor and part (9 limbs + hip-head)
+ * and d_mpjpe [2] f64 = (sum of joint errors, joints) -- the counters a multi-GPU run all-reduces. */
+int pam_eval_pcp(pam_handle* h, const int32_t* d_out_count, const float* d_out_joints, const double* d_gt,
+                 const uint8_t* d_gt_valid, int32_t S, int32_t T, int32_t P, int32_t max_tracks, int32_t remap_coco17,
+                 int32_t frame_begin, int32_t frame_end, double alpha, uint64_t* d_counters, double* d_mpjpe,
+                 void* stream);
+
 /* number of kernel launches issued through this handle so far (bench.py "gpu_launches") */
 int64_t pam_launch_count(const pam_handle* h);
 

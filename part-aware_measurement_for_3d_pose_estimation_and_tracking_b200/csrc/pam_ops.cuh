@@ -351,4 +351,97 @@ __global__ void k_epipolar_distance(const float* __restrict__ F, int V, const do
     out[(int64_t)it * 2 + 1] = d2;
 }
 
+// ---- section 8f-1: PCP / MPJPE counters of Evaluate3DPose_PCP (evalmodel.py:120-206) ------------------
+// One thread per (sequence, frame, ground-truth actor).  Predicted poses come straight from the
+// tracker's output tensors (count [S][T], joints [S][T][MT][J][3] f32); gt [S][T][P][14][3] f64 in
+// Shelf/Campus joint order, gt_valid [S][T][P].  remap 0: predictions already have the 14 Shelf joints;
+// remap 1: COCO-17 -> Shelf-14 with coco2shelf3D (eval/transformation.py:5-39).
+// counters [P][10][2] int64 = (correct, evaluated) per actor and bone (9 limbs + hip-head), summed over
+// all sequences / frames with atomics; mpjpe [2] f64 = (sum of per-joint errors, joints counted).
+__device__ __forceinline__ void to_shelf14(const float* __restrict__ p, int remap, double (*o)[3]) {
+    if (!remap) {
+        for (int j = 0; j < 14; ++j) for (int k = 0; k < 3; ++k) o[j][k] = (double)p[j * 3 + k];
+        return;
+    }
+    const int map[12] = {16, 14, 12, 11, 13, 15, 10, 8, 6, 5, 7, 9};
+    for (int j = 0; j < 12; ++j) for (int k = 0; k < 3; ++k) o[j][k] = (double)p[map[j] * 3 + k];
+    const double top[3] = {0.78, 0.5, 1.5}, bot[3] = {0.3, 0.4, 0.6};
+    for (int k = 0; k < 3; ++k) {
+        const double mid = (o[8][k] + o[9][k]) / 2.0, nose = (double)p[k];
+        o[13][k] = mid + (nose - mid) * top[k];
+        o[12][k] = mid + (nose - mid) * bot[k];
+    }
+}
+__device__ __forceinline__ double dist3(const double* a, const double* b) {
+    const double x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
+    return sqrt(x * x + y * y + z * z);
+}
+#define PAM_EVAL_MAX_P 64
+__global__ void __launch_bounds__(128)
+k_eval_pcp(const int* __restrict__ count, const float* __restrict__ joints, const double* __restrict__ gt,
+           const unsigned char* __restrict__ gt_valid, int S, int T, int P, int MT, int J, int remap,
+           int t0, int t1, double alpha, unsigned long long* __restrict__ counters, double* __restrict__ mpjpe) {
+    // block-local counters first (shared-memory atomics), one global atomic per counter per block
+    __shared__ unsigned int s_cnt[PAM_EVAL_MAX_P * 20];
+    __shared__ double s_err[4];
+    __shared__ unsigned int s_nj;
+    for (int i = threadIdx.x; i < P * 20; i += blockDim.x) s_cnt[i] = 0u;
+    if (threadIdx.x < 4) s_err[threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) s_nj = 0u;
+    __syncthreads();
+    const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    bool scored = false;
+    if (it < (int64_t)S * T * P) {
+        const int pid = (int)(it % P);
+        const int64_t st = it / P;
+        const int t = (int)(st % T);
+        if (t >= t0 && t < t1 && gt_valid[it]) {
+            unsigned int* cnt = s_cnt + pid * 20;
+            const int k = count[st];
+            if (k <= 0) {                  // "Cannot get any pose in frame": all ten parts count as errors
+                for (int b = 0; b < 10; ++b) atomicAdd(cnt + b * 2 + 1, 1u);
+            } else {
+                const double* g = gt + it * 14 * 3;
+                double best = 0.0, m[14][3], bm[14][3];
+                for (int q = 0; q < k; ++q) {
+                    to_shelf14(joints + ((int64_t)st * MT + q) * J * 3, remap, m);
+                    double d = 0.0;        // vectorize_distance: squared distance over all 42 coordinates
+                    for (int j = 0; j < 14; ++j)
+                        for (int c = 0; c < 3; ++c) { const double x = g[j * 3 + c] - m[j][c]; d += x * x; }
+                    if (q == 0 || d < best) {
+                        best = d;
+                        for (int j = 0; j < 14; ++j) for (int c = 0; c < 3; ++c) bm[j][c] = m[j][c];
+                    }
+                }
+                const int bones[9][2] = {{0, 1}, {1, 2}, {3, 4}, {4, 5}, {6, 7}, {7, 8}, {9, 10}, {10, 11}, {12, 13}};
+                for (int b = 0; b < 9; ++b) {
+                    const int s0 = bones[b][0], e0 = bones[b][1];
+                    const double len = dist3(g + e0 * 3, g + s0 * 3);
+                    if ((dist3(g + s0 * 3, bm[s0]) + dist3(g + e0 * 3, bm[e0])) / 2.0 <= alpha * len) atomicAdd(cnt + b * 2, 1u);
+                    atomicAdd(cnt + b * 2 + 1, 1u);
+                }
+                double gh[3], mh[3];
+                for (int c = 0; c < 3; ++c) { gh[c] = (g[2 * 3 + c] + g[3 * 3 + c]) / 2.0; mh[c] = (bm[2][c] + bm[3][c]) / 2.0; }
+                const double len = dist3(g + 12 * 3, gh);
+                if ((dist3(gh, mh) + dist3(g + 12 * 3, bm[12])) / 2.0 <= alpha * len) atomicAdd(cnt + 18, 1u);
+                atomicAdd(cnt + 19, 1u);
+                for (int j = 0; j < 14; ++j) e += dist3(g + j * 3, bm[j]);
+                scored = true;
+            }
+        }
+    }
+    // MPJPE: warp shuffle reduction, then one shared slot per warp
+    unsigned int nsc = __ballot_sync(0xffffffffu, scored);
+    for (int off = 16; off > 0; off >>= 1) e += __shfl_down_sync(0xffffffffu, e, off);
+    if ((threadIdx.x & 31) == 0) { s_err[threadIdx.x >> 5] = e; atomicAdd(&s_nj, 14u * __popc(nsc)); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P * 20; i += blockDim.x)
+        if (s_cnt[i]) atomicAdd(counters + i, (unsigned long long)s_cnt[i]);
+    if (threadIdx.x == 0 && s_nj) {
+        atomicAdd(mpjpe, s_err[0] + s_err[1] + s_err[2] + s_err[3]);
+        atomicAdd(mpjpe + 1, (double)s_nj);
+    }
+}
+
 }  // namespace pam
