@@ -81,6 +81,7 @@ struct TrackIO {
     unsigned char* out_nv;  // [S][T][MT][J]
     int* out_assoc;         // [S][T][V][D]
     int seq_frames;         // frames between consecutive sequences in every tensor above (>= T)
+    int* out_status;        // [S] final status word of each sequence, or null
 };
 
 #define PAM_TRACK_THREADS_MAX 256
@@ -136,6 +137,7 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
         PAM_MARK(8);
     }
     store_state(ctx, c, sh, g);
+    if (io.out_status && threadIdx.x == 0) io.out_status[s] = sh.hdr.status;
 #if defined(PAM_PHASE_TIMING)
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         static const char* nm[9] = {"1 age+reproj", "2 affinity", "3 assign", "4 add_pose+believe", "5 filter+dlt",
@@ -182,6 +184,8 @@ struct pam_handle {
     bool smem_opt_in = false;
     cudaStream_t ws_stream = nullptr, ws_in = nullptr, ws_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_k;
+    char* zc = nullptr;        // pinned, device-mapped staging of the small-job path
+    size_t zc_cap = 0;
     int64_t launches = 0;
     std::string err;
 };
@@ -265,6 +269,7 @@ int pam_destroy(pam_handle* h) {
     if (h->ws_out) cudaStreamDestroy(h->ws_out);
     for (auto e : h->ev_in) cudaEventDestroy(e);
     for (auto e : h->ev_k) cudaEventDestroy(e);
+    if (h->zc) cudaFreeHost(h->zc);
     delete h;
     return PAM_OK;
 }
@@ -335,7 +340,7 @@ int pam_track_sequences(pam_handle* h, void* d_state, int32_t S, int32_t T, int3
     if (!tracker_capable(h->cfg)) return fail(h, PAM_E_INVALID, "the stateful tracker handles at most 8 cameras");
     if (S == 0 || T == 0) return PAM_OK;
     CK(cudaSetDevice(h->device));
-    TrackIO io{d_dets, d_counts, d_out_count, d_out_ids, d_out_joints, d_out_nviews, d_out_assoc, T};
+    TrackIO io{d_dets, d_counts, d_out_count, d_out_ids, d_out_joints, d_out_nviews, d_out_assoc, T, nullptr};
     return launch_track(h, d_state, S, T, frame0, io, (cudaStream_t)stream);
 }
 
@@ -382,6 +387,44 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
         CK(cudaMemsetAsync(h->ws_state.p, 0, (size_t)c.seq_bytes * S, st));
         h->ws_S = S;
     }
+    // Small jobs (the per-frame drop-in API: S = T = 1): no staging copies at all.  Inputs are placed in
+    // pinned host memory that is mapped into the device address space; the kernel reads them and writes
+    // its results over PCIe directly, so a call costs one launch and one stream synchronisation.
+    {
+        auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+        const size_t o_dets = 0, o_counts = o_dets + up(b_dets), o_count = o_counts + up(b_counts);
+        const size_t o_ids = o_count + up(b_count), o_joints = o_ids + up(b_ids), o_nv = o_joints + up(b_joints);
+        const size_t o_assoc = o_nv + up(b_nv), o_status = o_assoc + up(b_assoc), total = o_status + up((size_t)S * 4);
+        if (total <= 256 * 1024) {
+            if (total > h->zc_cap) {
+                if (h->zc) cudaFreeHost(h->zc);
+                h->zc = nullptr; h->zc_cap = 0;
+                CK(cudaHostAlloc((void**)&h->zc, 256 * 1024, cudaHostAllocMapped));
+                h->zc_cap = 256 * 1024;
+            }
+            char* z = h->zc;
+            char* dz = nullptr;
+            CK(cudaHostGetDevicePointer((void**)&dz, z, 0));
+            memcpy(z + o_dets, h_dets, b_dets);
+            memcpy(z + o_counts, h_counts, b_counts);
+            TrackIO io{(const float*)(dz + o_dets), (const int32_t*)(dz + o_counts), (int32_t*)(dz + o_count),
+                       h_out_ids ? (int32_t*)(dz + o_ids) : nullptr, h_out_joints ? (float*)(dz + o_joints) : nullptr,
+                       h_out_nviews ? (uint8_t*)(dz + o_nv) : nullptr, h_out_assoc ? (int32_t*)(dz + o_assoc) : nullptr, T,
+                       (int*)(dz + o_status)};
+            int rc = launch_track(h, h->ws_state.p, S, T, frame0, io, st);
+            if (rc != PAM_OK) return rc;
+            CK(cudaStreamSynchronize(st));
+            memcpy(h_out_count, z + o_count, b_count);
+            if (h_out_ids) memcpy(h_out_ids, z + o_ids, b_ids);
+            if (h_out_joints) memcpy(h_out_joints, z + o_joints, b_joints);
+            if (h_out_nviews) memcpy(h_out_nviews, z + o_nv, b_nv);
+            if (h_out_assoc) memcpy(h_out_assoc, z + o_assoc, b_assoc);
+            const int32_t* stw = (const int32_t*)(z + o_status);
+            for (int s = 0; s < S; ++s)
+                if (stw[s] != 0) return pam_track_status(h, h->ws_state.p, S, nullptr, st);   // formats the message
+            return PAM_OK;
+        }
+    }
     CK(h->ws_dets.reserve(b_dets));
     CK(h->ws_counts.reserve(b_counts));
     CK(h->ws_count.reserve(b_count));
@@ -423,7 +466,7 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
                    h_out_ids ? (int32_t*)h->ws_ids.p + (size_t)t0 * c.max_trk : nullptr,
                    h_out_joints ? (float*)h->ws_joints.p + (size_t)t0 * (f_joints / 4) : nullptr,
                    h_out_nviews ? (uint8_t*)h->ws_nv.p + (size_t)t0 * f_nv : nullptr,
-                   h_out_assoc ? (int32_t*)h->ws_assoc.p + (size_t)t0 * (f_assoc / 4) : nullptr, T};
+                   h_out_assoc ? (int32_t*)h->ws_assoc.p + (size_t)t0 * (f_assoc / 4) : nullptr, T, nullptr};
         int rc = launch_track(h, h->ws_state.p, S, n, frame0 + t0, io, st);
         if (rc != PAM_OK) return rc;
         CK(cudaEventRecord(h->ev_k[k], st));

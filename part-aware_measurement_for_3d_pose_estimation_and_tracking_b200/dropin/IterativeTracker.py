@@ -61,16 +61,18 @@ class IterativeTracker(object):
         self.conf_threshold = self.args.conf_threshold
         self.num_joints = self.args.num_joints
         self.epi_threshold = self.args.epi_threshold
-        self.unmatched = dict()
-        self.tracks_ids = set()
+        self._pending = None
+        self._unmatched = dict()
+        self._ids_seen = set()
         self.build3D = None
         self._trk = None
         self._cams = None
         self._tracks_cache = None
 
     def track_restart(self):
-        self.unmatched = dict()
-        self.tracks_ids = set()
+        self._pending = None
+        self._unmatched = dict()
+        self._ids_seen = set()
         self._tracks_cache = None
         self._fresh = True
 
@@ -112,17 +114,30 @@ class IterativeTracker(object):
         k = int(self._out["count"][0, 0])
         self.last_ids = self._out["ids"][0, 0, :k].copy()
         self.last_joints = self._out["joints"][0, 0, :k].astype(np.float64)
-        self.tracks_ids.update(int(i) for i in self.last_ids)
-        # leftovers per camera, as the reference leaves them after init_target_GD (:56-61, :163-167)
-        for c, (camera, boxes, dets) in enumerate(zip(camera_list, boxes_list, detections_list)):
-            m = len(dets)
-            free = [d for d in range(m) if self._out["assoc"][0, 0, c, d] < 0]
-            kept = [np.asarray(dets[d]) for d in free]
-            if len(camera_list) >= 2:
-                kept = [d for d in kept if get_believe(d) > self.conf_threshold]
-            bx = np.asarray(boxes)[free] if len(np.asarray(boxes)) == m and m else np.asarray(boxes)
-            self.unmatched[camera.cid] = {'camera': camera, 'time': frame_id, 'bboxes': bx, 'detections': np.array(kept)}
+        self._pending = (frame_id, camera_list, boxes_list, detections_list, self._out["assoc"][0, 0].copy())
         return _time.time() - t0, 0.0, 0.0
+
+    @property
+    def unmatched(self):
+        """Leftover detections per camera, as the reference leaves them after ``init_target_GD``
+        (src/tracking/IterativeTracker.py:56-61, 163-167); built on first access after a frame."""
+        if self._pending is not None:
+            frame_id, camera_list, boxes_list, detections_list, assoc = self._pending
+            self._pending = None
+            for c, (camera, boxes, dets) in enumerate(zip(camera_list, boxes_list, detections_list)):
+                m = len(dets)
+                free = [d for d in range(m) if assoc[c, d] < 0]
+                kept = [np.asarray(dets[d]) for d in free]
+                if len(camera_list) >= 2:
+                    kept = [d for d in kept if get_believe(d) > self.conf_threshold]
+                bx = np.asarray(boxes)[free] if len(np.asarray(boxes)) == m and m else np.asarray(boxes)
+                self._unmatched[camera.cid] = {'camera': camera, 'time': frame_id, 'bboxes': bx, 'detections': np.array(kept)}
+        return self._unmatched
+
+    @unmatched.setter
+    def unmatched(self, value):
+        self._unmatched = value
+        self._pending = None
 
     @property
     def tracks(self):
@@ -131,5 +146,13 @@ class IterativeTracker(object):
         if self._tracks_cache is None:
             st = self._trk.read_state(host_path=True)[0]
             self._tracks_cache = [IterTrack(d, self._cams) for d in st["tracks"]]
-            self.tracks_ids.update(t.track_id for t in self._tracks_cache)
+            self._next_id = st["next_id"]
         return self._tracks_cache
+
+    @property
+    def tracks_ids(self):
+        """Every id handed out so far (the reference never prunes this set, :113)."""
+        if self._trk is None:
+            return set()
+        self.tracks  # refresh the state read-back
+        return set(range(getattr(self, "_next_id", 0)))

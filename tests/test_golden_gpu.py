@@ -38,7 +38,10 @@ def test_dropin_tracker_per_frame_api_reproduces_reference_stream():
         assert [r[0] for r in rep] == g["ids"][t, :k].tolist(), t
         for (tid, pose), ref in zip(rep, g["joints"][t, :k]):
             assert np.abs(pose - ref).max() < 5e-4
-    assert sorted(trk.tracks_ids) == sorted(set(g["ids"][g["ids"] >= 0].tolist()) | {tr.track_id for tr in trk.tracks})
+    ids = trk.tracks_ids                      # every id ever handed out, like the reference's never-pruned set
+    assert set(g["ids"][g["ids"] >= 0].tolist()) <= ids and {tr.track_id for tr in trk.tracks} <= ids
+    assert ids == set(range(len(ids)))
+    assert set(trk.unmatched.keys()) == set(range(len(cams)))
 
 
 def test_dropin_functions_match_reference_vectors():
