@@ -86,7 +86,7 @@ struct TrackIO {
 
 #define PAM_TRACK_THREADS_MAX 256
 
-template <int MAXT, int MINB>
+template <int MAXT, int MINB, int TEAM>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, int T, int frame0, const TrackIO io) {
     extern __shared__ double arena[];
@@ -126,7 +126,8 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
         if (t + 1 < T)
             stage_frame(dbuf + (cur ^ 1) * nfl_pad, cbuf + (cur ^ 1) * PAM_MAX_V, gd + (int64_t)(t + 1) * nfl,
                         gc + (t + 1) * c.V, nfl, c.V);
-        frame_step(ctx, c, sh, g, frame0 + t, dbuf + cur * nfl_pad, cbuf + cur * PAM_MAX_V, o);
+        if (TEAM > 1) frame_step<WarpTeam<TEAM>>(ctx, c, sh, g, frame0 + t, dbuf + cur * nfl_pad, cbuf + cur * PAM_MAX_V, o);
+        else frame_step<SoloTeam>(ctx, c, sh, g, frame0 + t, dbuf + cur * nfl_pad, cbuf + cur * PAM_MAX_V, o);
         if (o.count) o.count += 1;
         if (o.ids) o.ids += st_ids;
         if (o.joints) o.joints += st_joints;
@@ -176,6 +177,7 @@ struct pam_handle {
     int track_threads = 128;
     int track_minblocks = 0;   // 0 = choose per launch
     int num_sms = 148;
+    int track_team = 0;        // 0 = choose per launch
     DevBuf cam;              // packed camera constants
     CamConst cc{};
     // workspace of the *_host entry points
@@ -252,6 +254,8 @@ int pam_create(const pam_config* cfg, int device, pam_handle** out) {
         h->track_threads = want <= 64 ? 64 : (want <= 128 ? 128 : (want <= 192 ? 192 : 256));
     }
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+    const char* tm = getenv("PAM_TRACK_TEAM");
+    if (tm) { int v = atoi(tm); if (v == 1 || v == 2) h->track_team = v; }
     const char* mb = getenv("PAM_TRACK_MINBLOCKS");
     if (mb) { int v = atoi(mb); if (v == 4 || v == 6 || v == 8) h->track_minblocks = v; }
     *out = h;
@@ -310,13 +314,18 @@ typedef void (*track_kernel_t)(const DevCfg, const CamConst, char*, int, int, co
 
 // register budget variants: <= 128 threads with 4 / 6 / 8 CTAs per SM, or up to 256 threads
 static track_kernel_t pick_track_kernel(const pam_handle* h, int S) {
-    if (h->track_threads > 128) return k_track_sequences<256, 2>;
-    // few sequences: latency matters, take the full register budget; many: 6 CTAs per SM hide latency
-    const int mb = h->track_minblocks ? h->track_minblocks : (S > 4 * h->num_sms ? 6 : 4);
+    // few sequences: latency matters, take the full register budget; many: 6 CTAs per SM hide latency.
+    // Two lanes per (track, joint) (PAM_TRACK_TEAM=2) measured no faster than one on B200 (the phase is
+    // bound by the dependent FP64 chain of the solve, not by the work that can be split), so 1 is the default.
+    const bool many = S > 4 * h->num_sms;
+    const int mb = h->track_minblocks ? h->track_minblocks : (many ? 6 : 4);
+    const int team = h->track_team ? h->track_team : 1;
+    if (h->track_threads > 128) return team > 1 ? k_track_sequences<256, 2, 2> : k_track_sequences<256, 2, 1>;
+    if (team > 1) return mb >= 6 ? k_track_sequences<128, 6, 2> : k_track_sequences<128, 4, 2>;
     switch (mb) {
-        case 8: return k_track_sequences<128, 8>;
-        case 6: return k_track_sequences<128, 6>;
-        default: return k_track_sequences<128, 4>;
+        case 8: return k_track_sequences<128, 8, 1>;
+        case 6: return k_track_sequences<128, 6, 1>;
+        default: return k_track_sequences<128, 4, 1>;
     }
 }
 

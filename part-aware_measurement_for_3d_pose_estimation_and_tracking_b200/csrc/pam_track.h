@@ -208,6 +208,40 @@ struct HostCtx {
 #define PAM_MARK(k) do { } while (0)
 #endif
 
+// A "team" = W adjacent lanes that cooperate on one (track, joint) item in phase 5: they split the
+// view pairs of the epipolar test and the views of the Gram fold, and combine with warp shuffles
+// restricted to the team's own lanes.  W = 1 (host harness, throughput-oriented launches) does
+// everything on one lane.
+struct SoloTeam {
+    static constexpr int size = 1;
+    int rank = 0;
+    PAM_HD uint32_t or_u32(uint32_t x) const { return x; }
+    PAM_HD double sum_f64(double x) const { return x; }
+};
+#if defined(__CUDACC__)
+template <int W>
+struct WarpTeam {
+    static constexpr int size = W;
+    int rank;
+    unsigned mask;
+    __device__ __forceinline__ WarpTeam() {
+        const int lane = threadIdx.x & 31;
+        rank = lane & (W - 1);
+        mask = ((W >= 32) ? 0xffffffffu : ((1u << W) - 1u)) << (lane & ~(W - 1));
+    }
+    __device__ __forceinline__ uint32_t or_u32(uint32_t x) const {
+#pragma unroll
+        for (int off = W / 2; off > 0; off >>= 1) x |= __shfl_xor_sync(mask, x, off);
+        return x;
+    }
+    __device__ __forceinline__ double sum_f64(double x) const {
+#pragma unroll
+        for (int off = W / 2; off > 0; off >>= 1) x += __shfl_xor_sync(mask, x, off);
+        return x;
+    }
+};
+#endif
+
 #define PAM_FOR(i, N) PAM_NOUNROLL for (int i = ctx.tid(), _n_##i = (N), _s_##i = ctx.nthreads(); i < _n_##i; i += _s_##i)
 
 // camera constants: f32 in global memory (the reference's dtypes), widened once into shared.
@@ -253,18 +287,24 @@ PAM_HD void store_state(Ctx& ctx, const DevCfg& c, const SeqShared& sh, const Se
 // Weighted DLT over the surviving views (bit a of `alive`); T == nullptr means all ages 0.
 // Fresh-only systems go through the Gram/Cholesky fold; if that is judged too close to singular
 // (or any view is stale) the rows are folded again with Givens rotations.
-template <class CidT>
-PAM_HD void dlt_from_views(const DevCfg& c, const SeqShared& sh, int Vt, const CidT* cid, const int* T,
+template <class Team, class CidT>
+PAM_HD void dlt_from_views(const Team& tm, const DevCfg& c, const SeqShared& sh, int Vt, const CidT* cid, const int* T,
                            const double* u, const double* v, uint32_t alive, bool fresh, double* X) {
     DltAccum acc;
     int path = -1;
     if (fresh) {
         acc.reset(true);
-        PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
+        PAM_NOUNROLL for (int a = tm.rank; a < Vt; a += Team::size)
             if ((alive >> a) & 1u) acc.add_view(sh.Pc(cid[a]), u[a], v[a], c.w_age[0]);
+        if (Team::size > 1) {     // the Gram matrix is additive over views
+            acc.r00 = tm.sum_f64(acc.r00); acc.r01 = tm.sum_f64(acc.r01); acc.r02 = tm.sum_f64(acc.r02);
+            acc.r03 = tm.sum_f64(acc.r03); acc.r11 = tm.sum_f64(acc.r11); acc.r12 = tm.sum_f64(acc.r12);
+            acc.r13 = tm.sum_f64(acc.r13); acc.r22 = tm.sum_f64(acc.r22); acc.r23 = tm.sum_f64(acc.r23);
+            acc.r33 = tm.sum_f64(acc.r33);
+        }
         acc.solve(X, &path);
     }
-    if (path < 0) {
+    if (path < 0) {               // stale views or a near-singular Gram matrix: every lane folds all rows
         acc.reset(false);
         PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
             if ((alive >> a) & 1u) acc.add_view(sh.Pc(cid[a]), u[a], v[a], c.w_age[T ? T[a] : 0]);
@@ -275,21 +315,28 @@ PAM_HD void dlt_from_views(const DevCfg& c, const SeqShared& sh, int Vt, const C
 // Part-aware view filter + DLT for one joint of one track (update mode).
 //   views 0..Vt-1 in the track's dict order; cid/T per view; (u, v) per view; next = predicted joint.
 // Returns the number of surviving views; X = triangulated joint (or `next` when < 2 views).
-PAM_HD int joint_update(const DevCfg& c, const SeqShared& sh, int Vt, const int* cid, const int* T,
+template <class Team>
+PAM_HD int joint_update(const Team& tm, const DevCfg& c, const SeqShared& sh, int Vt, const int* cid, const int* T,
                         const double* u, const double* v, const double* next, double* X) {
     uint32_t conflict[PAM_MAX_V];
     PAM_NOUNROLL for (int a = 0; a < Vt; ++a) conflict[a] = 0u;
-    bool any = false;
+    int k = 0;
     PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
-        PAM_NOUNROLL for (int b = a + 1; b < Vt; ++b) {
+        PAM_NOUNROLL for (int b = a + 1; b < Vt; ++b, ++k) {
+            if (Team::size > 1 && (k & (Team::size - 1)) != tm.rank) continue;   // view pairs are dealt round-robin
             double dab = epi_dist_f64(sh.Fc(cid[a], cid[b]), u[a], v[a], u[b], v[b]);
             double dba = epi_dist_f64(sh.Fc(cid[b], cid[a]), u[b], v[b], u[a], v[a]);
             double D = (dab + dba) / 2.0;
             double A = 1.0 - D * c.inv_joint_thr;
-            if (A < 0.0) { conflict[a] |= (1u << b); any = true; }
+            if (A < 0.0) conflict[a] |= (1u << b);
         }
+    uint32_t any = 0u;
+    PAM_NOUNROLL for (int a = 0; a < Vt; ++a) {
+        conflict[a] = tm.or_u32(conflict[a]);
+        any |= conflict[a];
+    }
     uint32_t alive = (Vt >= 32) ? 0xffffffffu : ((1u << Vt) - 1u);
-    if (any) {
+    if (any) {                     // identical on every lane of the team
         double rd[PAM_MAX_V];
         PAM_NOUNROLL for (int a = 0; a < Vt; ++a) rd[a] = 0.0;
         PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
@@ -309,7 +356,7 @@ PAM_HD int joint_update(const DevCfg& c, const SeqShared& sh, int Vt, const int*
     bool fresh = true;
     PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
         if (((alive >> a) & 1u) && T[a] != 0) fresh = false;
-    dlt_from_views(c, sh, Vt, cid, T, u, v, alive, fresh, X);
+    dlt_from_views(tm, c, sh, Vt, cid, T, u, v, alive, fresh, X);
     return nv;
 }
 
@@ -341,7 +388,7 @@ PAM_HD int joint_init(const DevCfg& c, const SeqShared& sh, int Vt, const signed
     }
     const int nv = popcount32(alive);
     if (nv < 2) return nv;
-    dlt_from_views(c, sh, Vt, cid, (const int*)nullptr, u, v, alive, true, X);
+    dlt_from_views(SoloTeam(), c, sh, Vt, cid, (const int*)nullptr, u, v, alive, true, X);
     return nv;
 }
 
@@ -388,7 +435,7 @@ PAM_HD bool track_reported(const DevCfg& c, const SeqShared& sh, int i) {
 
 // `dets`/`counts` point at this frame's detections (staged in shared memory by the kernel).
 // The caller must synchronise the block after frame_step returns.
-template <class Ctx>
+template <class Team, class Ctx>
 PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal& g, int frame,
                        const float* dets /* [V][D][J][3] */, const int* counts /* [V] */, const FrameOut& out) {
     const int V = c.V, J = c.J, D = c.D, MT = c.max_trk;
@@ -554,36 +601,42 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
 
     // ---- phase 5: per (track, joint): part-aware view filter + DLT (IterativeTracker.py:337-369);
     //      persist the matched detections as the tracks' newest views; unmatched lists ---------
-    PAM_FOR(it, n * J) {
-        const int i = fast_div(it, c.inv_J), j = it - i * J;
-        if (!sh.do_update[i]) continue;
-        const int s = sh.hdr.order[i];
-        const TrkMeta& t = sh.trk[s];
-        const double* Xl = g.hist + ((int64_t)(s * PAM_HIST + sh.last[i]) * J + j) * 3;
-        const float* vel = g.vel + (int64_t)(s * J + j) * 3;
-        const float fdt = (float)sh.dt[i];
-        double next[3];
-        for (int k = 0; k < 3; ++k) next[k] = Xl[k] + (double)(vel[k] * fdt);
-        int cid[PAM_MAX_V], T[PAM_MAX_V];
-        double u[PAM_MAX_V], v[PAM_MAX_V];
-        const int Vt = sh.gv_n[i];
-        PAM_NOUNROLL for (int a = 0; a < Vt; ++a) {
-            const int k = sh.gv_idx[i][a];
-            const int cam = t.view_cid[k];
-            cid[a] = cam;
-            T[a] = frame - t.view_time[k];
-            // a view matched this frame is read straight from the staged detections
-            const float* q = (T[a] == 0) ? dets + ((int64_t)(cam * D + sh.t2d[cam][i]) * J + j) * 3
-                                         : g.view + ((int64_t)(s * V + k) * J + j) * 3;
-            v[a] = (double)q[0];
-            u[a] = (double)q[1];
+    {
+        const Team tm;
+        const int teams = ctx.nthreads() / Team::size;
+        PAM_NOUNROLL for (int it = ctx.tid() / Team::size; it < n * J; it += teams) {
+            const int i = fast_div(it, c.inv_J), j = it - i * J;
+            if (!sh.do_update[i]) continue;          // uniform within a team
+            const int s = sh.hdr.order[i];
+            const TrkMeta& t = sh.trk[s];
+            const double* Xl = g.hist + ((int64_t)(s * PAM_HIST + sh.last[i]) * J + j) * 3;
+            const float* vel = g.vel + (int64_t)(s * J + j) * 3;
+            const float fdt = (float)sh.dt[i];
+            double next[3];
+            for (int k = 0; k < 3; ++k) next[k] = Xl[k] + (double)(vel[k] * fdt);
+            int cid[PAM_MAX_V], T[PAM_MAX_V];
+            double u[PAM_MAX_V], v[PAM_MAX_V];
+            const int Vt = sh.gv_n[i];
+            PAM_NOUNROLL for (int a = 0; a < Vt; ++a) {
+                const int k = sh.gv_idx[i][a];
+                const int cam = t.view_cid[k];
+                cid[a] = cam;
+                T[a] = frame - t.view_time[k];
+                // a view matched this frame is read straight from the staged detections
+                const float* q = (T[a] == 0) ? dets + ((int64_t)(cam * D + sh.t2d[cam][i]) * J + j) * 3
+                                             : g.view + ((int64_t)(s * V + k) * J + j) * 3;
+                v[a] = (double)q[0];
+                u[a] = (double)q[1];
+            }
+            double X[3];
+            const int nv = joint_update(tm, c, sh, Vt, cid, T, u, v, next, X);
+            if (tm.rank == 0) {
+                sh.nvj[i][j] = (unsigned char)nv;
+                if (nv < 2) ctx.atomic_inc(&sh.fail[i]);
+                double* r = sh.raw + (int64_t)(i * J + j) * 3;
+                r[0] = X[0]; r[1] = X[1]; r[2] = X[2];
+            }
         }
-        double X[3];
-        const int nv = joint_update(c, sh, Vt, cid, T, u, v, next, X);
-        sh.nvj[i][j] = (unsigned char)nv;
-        if (nv < 2) ctx.atomic_inc(&sh.fail[i]);
-        double* r = sh.raw + (int64_t)(i * J + j) * 3;
-        r[0] = X[0]; r[1] = X[1]; r[2] = X[2];
     }
     {   // J3 consecutive floats per matched (camera, track) pair; lanes stride over the elements
         const int lanes = (ctx.nthreads() >= 32) ? 32 : ctx.nthreads();

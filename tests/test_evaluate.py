@@ -72,9 +72,11 @@ def test_oracle_pcp_matches_unmodified_reference(tmp_path):
         ref_check, _ = mod.Evaluate3DPose_PCP([[0, T]], str(tmp_path / "pred.pkl"), gt_path=str(tmp_path), dataset_name="Shelf")
     finally:
         sys.path[:] = saved_path
-        for k in list(sys.modules):
-            if k not in saved_mods:
-                del sys.modules[k]
+        for k in ("natsort", "motmetrics", "prettytable", "matplotlib", "matplotlib.pyplot", "dataset", "_init_path",
+                  "ref_evalmodel", "transformation", "numeric"):
+            sys.modules.pop(k, None)
+            if k in saved_mods:
+                sys.modules[k] = saved_mods[k]
     mine = oeval.pcp_check([np.transpose(p, (0, 2, 1)) for p in pred], gt14, valid, range(T), to_shelf=oeval.coco2shelf3D)
     assert np.array_equal(ref_check, mine)
     assert (mine > 0).sum() > 300 and (mine < 0).sum() > 30

@@ -33,8 +33,9 @@ base = None
 agg = collections.defaultdict(lambda: [0, 0, collections.Counter()])
 funcs = sorted({f for f, _ in addr2line})
 # kernel function = the one whose mangled name contains the kernel's base name
-kbase = re.match(r"(\w+)", kname).group(1)
-kfunc = [f for f in funcs if kbase in f][0]
+kbase = re.match(r"(\w+)", kname.replace("void ", "")).group(1)
+cands = [f for f in funcs if kbase in f]
+kfunc = ([f for f in cands if os.environ.get("KVARIANT", "") in f] or cands)[0]
 for r in rows[2:]:
     if len(r) <= iex: continue
     a = int(r[ia], 16) if r[ia].startswith("0x") else int(r[ia])
