@@ -219,12 +219,16 @@ PAM_HD double ray_point_distance(const double* RK, const double* pos, double u, 
 // system never exists in memory: rows are folded, as they are produced, into the 10 entries of the
 // upper-triangular 4x4 factor R with A^T A = R^T R, and the singular vector is extracted from R.
 //
-//   fold      fresh views only (all weights 1):  Gram matrix + Cholesky      (10 FMA per row)
-//             any stale view (weights e^{-lambda_t T} down to 3e-7):  streaming Givens QR, which
-//             keeps the relative accuracy of the tiny rows that a Gram matrix would lose
+//   fold      Gram matrix + Cholesky (10 FMA per row) while the pivots stay above 1e-6 of the
+//             diagonal; otherwise (systems resting on views 2-3 frames old, weights e^{-lambda_t T}
+//             down to 3e-7, or noise-free data) streaming Givens QR, which keeps the relative
+//             accuracy of the tiny rows that a Gram matrix would lose
 //   extract   inverse iteration with R (two triangular solves per step, converges like
 //             (sigma4/sigma3)^2); if it has not settled in 8 steps, or a pivot is degenerate,
 //             one-sided Jacobi SVD of R (unconditionally robust)
+#if defined(PAM_COUNT_ITERS) && !defined(__CUDA_ARCH__)
+static long long g_invit_steps = 0, g_invit_calls = 0;
+#endif
 struct DltAccum {
     double r00, r01, r02, r03, r11, r12, r13, r22, r23, r33;   // Gram entries, then R
     bool gram;
@@ -286,13 +290,13 @@ struct DltAccum {
         double i0 = rsqrt_f64(r00);
         r00 *= i0; r01 *= i0; r02 *= i0; r03 *= i0;
         double t11 = r11 - r01 * r01;
-        if (!(t11 > 1e-9 * g11)) return false;
+        if (!(t11 > 1e-6 * g11)) return false;
         double i1 = rsqrt_f64(t11);
         r11 = t11 * i1;
         r12 = (r12 - r01 * r02) * i1;
         r13 = (r13 - r01 * r03) * i1;
         double t22 = r22 - r02 * r02 - r12 * r12;
-        if (!(t22 > 1e-9 * g22)) return false;
+        if (!(t22 > 1e-6 * g22)) return false;
         double i2 = rsqrt_f64(t22);
         r22 = t22 * i2;
         r23 = (r23 - r02 * r03 - r12 * r13) * i2;
@@ -304,6 +308,9 @@ struct DltAccum {
 
     // inverse iteration on R^T R; x = homogeneous solution (unit norm).  false = not converged.
     PAM_HD bool invit(double* x) const {
+#if defined(PAM_COUNT_ITERS) && !defined(__CUDA_ARCH__)
+        ++g_invit_calls;
+#endif
         if (r00 == 0.0 || r11 == 0.0 || r22 == 0.0 || r33 == 0.0) return false;
         const double i0 = rcp_f64(r00), i1 = rcp_f64(r11), i2 = rcp_f64(r22), i3 = rcp_f64(r33);
         // start from R^-1 e4 (the direction R shrinks most when r33 is its smallest pivot)
@@ -328,6 +335,9 @@ struct DltAccum {
             z0 *= inv; z1 *= inv; z2 *= inv; z3 *= inv;
             double e0 = z0 - x0, e1 = z1 - x1, e2 = z2 - x2, e3 = z3 - x3;
             x0 = z0; x1 = z1; x2 = z2; x3 = z3;
+#if defined(PAM_COUNT_ITERS) && !defined(__CUDA_ARCH__)
+            ++g_invit_steps;
+#endif
             if (e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3 <= 1e-26) { ok = true; break; }
         }
         x[0] = x0; x[1] = x1; x[2] = x2; x[3] = x3;

@@ -277,7 +277,7 @@ __global__ void k_triangulate(const float* __restrict__ P, const double* __restr
     const bool work = active && nv >= 2;
     DltAccum acc;
     int path = -1;
-    if (fresh) {
+    {
         acc.reset(true);
         if (work)
             for (int a = lane; a < Vt; a += LANES) {
@@ -285,7 +285,7 @@ __global__ void k_triangulate(const float* __restrict__ P, const double* __restr
                 double Pm[12];
                 load12(P + cam[(int64_t)b * Vt + a] * 12, Pm);
                 const double* q = pose + (((int64_t)b * Vt + a) * J + j) * 3;
-                acc.add_view(Pm, q[1], q[0], 1.0);
+                acc.add_view(Pm, q[1], q[0], w[(int64_t)b * Vt + a]);
             }
         if (LANES > 1) {
 #pragma unroll

@@ -289,22 +289,25 @@ PAM_HD void store_state(Ctx& ctx, const DevCfg& c, const SeqShared& sh, const Se
 // (or any view is stale) the rows are folded again with Givens rotations.
 template <class Team, class CidT>
 PAM_HD void dlt_from_views(const Team& tm, const DevCfg& c, const SeqShared& sh, int Vt, const CidT* cid, const int* T,
-                           const double* u, const double* v, uint32_t alive, bool fresh, double* X) {
+                           const double* u, const double* v, uint32_t alive, double* X) {
+    // Gram / Cholesky fold first, stale views included with their weights e^{-lambda_t T}: as long as
+    // the Cholesky pivots stay above 1e-6 of the diagonal (two fresh views, or one fresh view plus views
+    // one frame old) the squared system resolves the solution to < 1e-10 relative.  Otherwise -- only
+    // views two or three frames old next to at most one fresh view, or a noise-free system -- the rows
+    // are folded again with Givens rotations, which keep the relative accuracy of the tiny rows.
     DltAccum acc;
     int path = -1;
-    if (fresh) {
-        acc.reset(true);
-        PAM_NOUNROLL for (int a = tm.rank; a < Vt; a += Team::size)
-            if ((alive >> a) & 1u) acc.add_view(sh.Pc(cid[a]), u[a], v[a], c.w_age[0]);
-        if (Team::size > 1) {     // the Gram matrix is additive over views
-            acc.r00 = tm.sum_f64(acc.r00); acc.r01 = tm.sum_f64(acc.r01); acc.r02 = tm.sum_f64(acc.r02);
-            acc.r03 = tm.sum_f64(acc.r03); acc.r11 = tm.sum_f64(acc.r11); acc.r12 = tm.sum_f64(acc.r12);
-            acc.r13 = tm.sum_f64(acc.r13); acc.r22 = tm.sum_f64(acc.r22); acc.r23 = tm.sum_f64(acc.r23);
-            acc.r33 = tm.sum_f64(acc.r33);
-        }
-        acc.solve(X, &path);
+    acc.reset(true);
+    PAM_NOUNROLL for (int a = tm.rank; a < Vt; a += Team::size)
+        if ((alive >> a) & 1u) acc.add_view(sh.Pc(cid[a]), u[a], v[a], c.w_age[T ? T[a] : 0]);
+    if (Team::size > 1) {     // the Gram matrix is additive over views
+        acc.r00 = tm.sum_f64(acc.r00); acc.r01 = tm.sum_f64(acc.r01); acc.r02 = tm.sum_f64(acc.r02);
+        acc.r03 = tm.sum_f64(acc.r03); acc.r11 = tm.sum_f64(acc.r11); acc.r12 = tm.sum_f64(acc.r12);
+        acc.r13 = tm.sum_f64(acc.r13); acc.r22 = tm.sum_f64(acc.r22); acc.r23 = tm.sum_f64(acc.r23);
+        acc.r33 = tm.sum_f64(acc.r33);
     }
-    if (path < 0) {               // stale views or a near-singular Gram matrix: every lane folds all rows
+    acc.solve(X, &path);
+    if (path < 0) {
         acc.reset(false);
         PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
             if ((alive >> a) & 1u) acc.add_view(sh.Pc(cid[a]), u[a], v[a], c.w_age[T ? T[a] : 0]);
@@ -353,10 +356,7 @@ PAM_HD int joint_update(const Team& tm, const DevCfg& c, const SeqShared& sh, in
         X[0] = next[0]; X[1] = next[1]; X[2] = next[2];
         return nv;
     }
-    bool fresh = true;
-    PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
-        if (((alive >> a) & 1u) && T[a] != 0) fresh = false;
-    dlt_from_views(tm, c, sh, Vt, cid, T, u, v, alive, fresh, X);
+    dlt_from_views(tm, c, sh, Vt, cid, T, u, v, alive, X);
     return nv;
 }
 
@@ -388,7 +388,7 @@ PAM_HD int joint_init(const DevCfg& c, const SeqShared& sh, int Vt, const signed
     }
     const int nv = popcount32(alive);
     if (nv < 2) return nv;
-    dlt_from_views(SoloTeam(), c, sh, Vt, cid, (const int*)nullptr, u, v, alive, true, X);
+    dlt_from_views(SoloTeam(), c, sh, Vt, cid, (const int*)nullptr, u, v, alive, X);
     return nv;
 }
 

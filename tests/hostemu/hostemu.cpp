@@ -70,9 +70,9 @@ extern "C" int hostemu_dlt(int n, int V, const double* P, const double* uv, cons
         for (int a = 0; a < V; ++a) if (keep[i * V + a] && w[i * V + a] != 1.0) fresh = false;
         DltAccum acc;
         int how = -1;
-        if (mode == 0 && fresh) {
+        if (mode == 0) {
             acc.reset(true);
-            for (int a = 0; a < V; ++a) if (keep[i * V + a]) acc.add_view(P + a * 12, uv[(i * V + a) * 2], uv[(i * V + a) * 2 + 1], 1.0);
+            for (int a = 0; a < V; ++a) if (keep[i * V + a]) acc.add_view(P + a * 12, uv[(i * V + a) * 2], uv[(i * V + a) * 2 + 1], w[i * V + a]);
             acc.solve(X + i * 3, &how);
             if (how >= 0) how += 10;
         }
@@ -86,3 +86,7 @@ extern "C" int hostemu_dlt(int n, int V, const double* P, const double* uv, cons
     }
     return 0;
 }
+
+#if defined(PAM_COUNT_ITERS)
+extern "C" void hostemu_invit_stats(long long* steps, long long* calls) { *steps = pam::g_invit_steps; *calls = pam::g_invit_calls; }
+#endif
