@@ -88,6 +88,102 @@ __global__ void k_assign(const double* __restrict__ cost, int B, int nr, int nc,
     for (int i = 0; i < nr; ++i) col4row[(int64_t)b * nr + i] = out[i];
 }
 
+// ---- a4, large problems: one WARP per assignment problem ----------------------------------------------
+// Same shortest-augmenting-path algorithm (Crouse 2016) as lsap_solve, with the scan over the columns
+// done by the 32 lanes in parallel: lane l owns columns l and l + 32 (dual v, shortest-path cost, path,
+// row4col) and rows l and l + 32 (dual u, col4row); the minimum over the unscanned columns is a warp
+// shuffle reduction.  Among equal minima an unassigned column is preferred (as scipy does), then the
+// lowest column index (scipy: scan order of its `remaining` list), so with exact ties a different but
+// equally optimal assignment may be returned.  nr, nc <= 64.
+__device__ __forceinline__ double warp_pick(double a0, double a1, int lane, int k) {
+    // value held by lane (k & 31) in register (k >> 5)
+    const double x0 = __shfl_sync(0xffffffffu, a0, k & 31), x1 = __shfl_sync(0xffffffffu, a1, k & 31);
+    return (k >> 5) ? x1 : x0;
+}
+__device__ __forceinline__ int warp_pick(int a0, int a1, int lane, int k) {
+    const int x0 = __shfl_sync(0xffffffffu, a0, k & 31), x1 = __shfl_sync(0xffffffffu, a1, k & 31);
+    return (k >> 5) ? x1 : x0;
+}
+__global__ void __launch_bounds__(128)
+k_assign_warp(const double* __restrict__ cost, int B, int nr0, int nc0, int maximize, int* __restrict__ col4row_out) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const double* C = cost + (int64_t)b * nr0 * nc0;
+    const double sgn = maximize ? -1.0 : 1.0;
+    const bool tr = nc0 < nr0;
+    const int nr = tr ? nc0 : nr0, nc = tr ? nr0 : nc0;
+    auto cst = [&](int i, int j) { return sgn * (tr ? C[j * nc0 + i] : C[i * nc0 + j]); };
+    const double INF = HUGE_VAL;
+    double u[2] = {0.0, 0.0}, v[2] = {0.0, 0.0}, sp[2];
+    int c4r[2] = {-1, -1}, r4c[2] = {-1, -1}, path[2] = {-1, -1};
+    for (int cur = 0; cur < nr; ++cur) {
+        double minVal = 0.0;
+        int i = cur, sink = -1;
+        uint32_t sc = 0u;                       // bit k: my column lane + 32 k is scanned
+        uint32_t sr0 = 0u, sr1 = 0u;            // rows in SR (replicated on every lane)
+        sp[0] = sp[1] = INF;
+        while (sink < 0) {
+            if (i < 32) sr0 |= 1u << i; else sr1 |= 1u << (i - 32);
+            const double ui = warp_pick(u[0], u[1], lane, i);
+            double best = INF;
+            int bestj = -1, bestfree = 0;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int j = lane + 32 * k;
+                if (j >= nc || ((sc >> k) & 1u)) continue;
+                const double r = minVal + cst(i, j) - ui - v[k];
+                if (r < sp[k]) { path[k] = i; sp[k] = r; }
+                const int fr = (r4c[k] == -1) ? 1 : 0;
+                if (sp[k] < best || (sp[k] == best && fr > bestfree)) { best = sp[k]; bestj = j; bestfree = fr; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                const int oj = __shfl_xor_sync(0xffffffffu, bestj, off), of = __shfl_xor_sync(0xffffffffu, bestfree, off);
+                const bool take = (oj >= 0) && (bestj < 0 || ob < best || (ob == best && (of > bestfree || (of == bestfree && oj < bestj))));
+                if (take) { best = ob; bestj = oj; bestfree = of; }
+            }
+            minVal = best;
+            if (bestj < 0 || minVal == INF) { sink = -2; break; }      // infeasible
+            if ((bestj & 31) == lane) sc |= 1u << (bestj >> 5);
+            if (bestfree) sink = bestj;
+            else i = warp_pick(r4c[0], r4c[1], lane, bestj);
+        }
+        if (sink == -2) break;
+        // dual updates
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int r = lane + 32 * k;
+            // every lane takes part in the shuffles; only rows in SR (other than cur) are updated
+            const int col = (r < nr && c4r[k] >= 0) ? c4r[k] : 0;
+            const double spc = warp_pick(sp[0], sp[1], lane, col);
+            const bool in_sr = r < nr && (((k ? sr1 : sr0) >> lane) & 1u);
+            if (in_sr && r != cur) u[k] += minVal - spc;
+            if (r == cur) u[k] += minVal;
+            if ((sc >> k) & 1u) v[k] -= minVal - sp[k];
+        }
+        // augment along the path
+        int j = sink;
+        while (true) {
+            const int pi = warp_pick(path[0], path[1], lane, j);
+            if ((j & 31) == lane) r4c[j >> 5] = pi;
+            const int old = warp_pick(c4r[0], c4r[1], lane, pi);
+            if ((pi & 31) == lane) c4r[pi >> 5] = j;
+            j = old;
+            if (pi == cur) break;
+        }
+    }
+    // rows of the ORIGINAL problem
+    if (!tr) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { const int r = lane + 32 * k; if (r < nr0) col4row_out[(int64_t)b * nr0 + r] = c4r[k]; }
+    } else {
+        // c4r maps original column -> original row; unassigned original rows stay -1 (pre-set by the host)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { const int r = lane + 32 * k; if (r < nr && c4r[k] >= 0) col4row_out[(int64_t)b * nr0 + c4r[k]] = r; }
+    }
+}
+
 // ---- a6: symmetric point-to-epipolar-line distances, float64 form ----------------------------------
 // pose [M][J][3] (v,u,conf), cam [M]; D [M][M][J], mean [M][M]; same-camera pairs use F = 0.
 __global__ void k_epipolar_pairs(const float* __restrict__ F, int V, const double* __restrict__ pose,
