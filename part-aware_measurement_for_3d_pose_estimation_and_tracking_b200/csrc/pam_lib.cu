@@ -445,9 +445,12 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
     // the kernel of chunk k (three streams; tracker state stays in HBM between the chunk launches).
     if (!h->ws_in) CK(cudaStreamCreateWithFlags(&h->ws_in, cudaStreamNonBlocking));
     if (!h->ws_out) CK(cudaStreamCreateWithFlags(&h->ws_out, cudaStreamNonBlocking));
-    int nchunks = T / 256;
+    int nchunks = T / 50;   // PCIe-bound: more, smaller chunks shorten the pipeline fill and drain
+    const char* nce = getenv("PAM_HOST_CHUNKS");
+    if (nce) nchunks = atoi(nce);
     if (nchunks < 1) nchunks = 1;
-    if (nchunks > 16) nchunks = 16;
+    if (nchunks > 64) nchunks = 64;
+    if (nchunks > T) nchunks = T;
     while ((int)h->ev_in.size() < nchunks + 1) {
         cudaEvent_t e1, e2;
         CK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
