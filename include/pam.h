@@ -192,6 +192,18 @@ int pam_triangulate(pam_handle* h, const double* d_pose, const int32_t* d_cam, c
 int pam_ray_distance(pam_handle* h, int32_t camera, const double* d_uv, const double* d_points3d_or_null, int32_t n,
                      double* d_dist_or_null, double* d_dirs_or_null, void* stream);
 
+/* get_believe (utils/calculate.py:8-14), batched: d_pose [batch][J][3] f64 -> d_out [batch] f64 mean
+ * confidence over the joints with conf >= 0 (NaN when there is none). */
+int pam_mean_confidence(pam_handle* h, const double* d_pose, int32_t batch, double* d_out, void* stream);
+
+/* Hypothesis.calculate_cost (tracking/hypothesis.py:53-68) of one hypothesis -- d_hyp_pose
+ * [n_views][J][3] f64, d_hyp_cam [n_views] i32 -- against `batch` candidate detections d_other_pose
+ * [batch][J][3] f64 of camera other_cam -> d_cost [batch] f64, d_veto [batch] u8 (uses
+ * cfg.epi_threshold and cfg.veto_believe). */
+int pam_hypothesis_cost(pam_handle* h, const double* d_hyp_pose, const int32_t* d_hyp_cam, int32_t n_views,
+                        const double* d_other_pose, int32_t other_cam, int32_t batch, double* d_cost, uint8_t* d_veto,
+                        void* stream);
+
 /* PCP / MPJPE counters of Evaluate3DPose_PCP (evalmodel.py:120-206, eval/transformation.py:5-39,
  * eval/numeric.py:5-25) straight from the tracker's output tensors: d_out_count [S][T], d_out_joints
  * [S][T][max_tracks][J][3] f32; d_gt [S][T][P][14][3] f64 (Shelf/Campus joint order), d_gt_valid

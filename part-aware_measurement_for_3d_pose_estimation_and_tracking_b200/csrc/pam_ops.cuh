@@ -447,6 +447,53 @@ __global__ void k_epipolar_distance(const float* __restrict__ F, int V, const do
     out[(int64_t)it * 2 + 1] = d2;
 }
 
+// ---- a16: get_believe (utils/calculate.py:8-14), batched: mean confidence over joints with conf >= 0 ----
+__global__ void k_mean_confidence(const double* __restrict__ pose, int B, int J, double* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double kept[PAM_MAX_J];
+    int nk = 0;
+    for (int j = 0; j < J; ++j) {
+        const double w = pose[((int64_t)b * J + j) * 3 + 2];
+        if (w >= 0.0) kept[nk++] = w;
+    }
+    out[b] = np_sum(kept, nk) / (double)nk;      // 0/0 -> NaN like np.mean([])
+}
+
+// ---- a16: Hypothesis.calculate_cost (tracking/hypothesis.py:53-68) of ONE hypothesis (k views) against
+// B candidate detections of camera `ocam`: cost [B], veto [B] ------------------------------------------
+__global__ void k_hypothesis_cost(const float* __restrict__ F, int V, const double* __restrict__ hpose,
+                                  const int* __restrict__ hcam, int k, const double* __restrict__ opose, int ocam, int B,
+                                  int J, double epi_thr, double veto_believe, double* __restrict__ cost,
+                                  unsigned char* __restrict__ veto) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double* o = opose + (int64_t)b * J * 3;
+    double kept[PAM_MAX_J];
+    int nk = 0;
+    for (int j = 0; j < J; ++j) if (o[j * 3 + 2] >= 0.0) kept[nk++] = o[j * 3 + 2];
+    const double believe = np_sum(kept, nk) / (double)nk;
+    double total = 0.0;
+    bool vt = false;
+    for (int q = 0; q < k; ++q) {
+        double Fm[9];
+        load9(F + ((int64_t)hcam[q] * V + ocam) * 9, Fm);
+        const double* p = hpose + (int64_t)q * J * 3;
+        NpSumStream<double> acc;
+        acc.begin(J);
+        for (int j = 0; j < J; ++j) {
+            double d1, d2;
+            epi_pair_cv(Fm, p[j * 3 + 1], p[j * 3], o[j * 3 + 1], o[j * 3], d1, d2);
+            acc.push((d1 * p[j * 3 + 2] + d2 * o[j * 3 + 2]) / 2.0);
+        }
+        const double pc = acc.total() / (double)J / epi_thr;
+        total += pc;
+        if (pc > 1.0 && believe > veto_believe) vt = true;
+    }
+    cost[b] = total / (double)k;
+    veto[b] = vt ? 1 : 0;
+}
+
 // ---- section 8f-1: PCP / MPJPE counters of Evaluate3DPose_PCP (evalmodel.py:120-206) ------------------
 // One thread per (sequence, frame, ground-truth actor).  Predicted poses come straight from the
 // tracker's output tensors (count [S][T], joints [S][T][MT][J][3] f32); gt [S][T][P][14][3] f64 in

@@ -7,10 +7,10 @@ from _pkg import ops as _ops
 
 
 def get_believe(points2d):
-    """Mean confidence of the joints with conf >= 0 (src/utils/calculate.py:8-14).  A <= 32-element
-    mean: host-side glue here; inside the tracker kernel it is phase 4 of csrc/pam_track.h."""
-    kept = [p[2] for p in points2d if p[2] >= 0]
-    return np.mean(kept)
+    """Mean confidence of the joints with conf >= 0 (src/utils/calculate.py:8-14) -> ``pam_mean_confidence``."""
+    pts = np.asarray(points2d, dtype=np.float64)
+    cam = _single_camera(np.eye(3), np.zeros(3))
+    return float(_ops.get_ops([cam], pts.shape[0]).mean_confidence(pts[None])[0])
 
 
 def _single_camera(RK_INV, position):
@@ -44,12 +44,14 @@ def line2point_distance_3D(camera_position, directions, points3d):
 
 
 def line2line_distance_3D(pt1, directions1, pt2, directions2):
-    """src/utils/calculate.py:20-24 (not on the live path; kept for the API surface)."""
+    """src/utils/calculate.py:20-24.  No caller anywhere in the reference (dead code); kept as plain
+    numpy only so that ``from calculate import line2line_distance_3D`` (matching.py:9) still resolves."""
     n = np.cross(directions1, directions2)
     n = n / np.linalg.norm(n, axis=1).reshape(-1, 1)
     return np.abs(np.sum(n * (pt1 - pt2), axis=1))
 
 
 def line_to_point_distance(a, b, c, x, y):
-    """ufunc of src/utils/calculate.py:16-18 (imported by the reference, never called)."""
+    """ufunc of src/utils/calculate.py:16-18: imported at matching.py:9 but never called (dead code);
+    plain numpy so the import resolves."""
     return np.abs(a * x + b * y + c) / np.sqrt(np.square(a) + np.square(b))

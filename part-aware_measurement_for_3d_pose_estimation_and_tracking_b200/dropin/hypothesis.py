@@ -23,22 +23,13 @@ class Hypothesis:
         self.poses.append(o_pose)
 
     def calculate_cost(self, o_cam, o_pose):
-        """-> (cost, veto) (src/tracking/hypothesis.py:53-68); the epipolar distances of all views
-        against the candidate are evaluated in one batched launch."""
+        """-> (cost, veto) (src/tracking/hypothesis.py:53-68) via ``pam_hypothesis_cost``."""
         cams = list(self.cams) + [o_cam]
-        o = _ops.get_ops(cams, self.joints)
+        o = _ops.get_ops(cams, self.joints, dict(epi_threshold=self.threshold))
         k = len(self.poses)
-        mine = np.asarray(self.poses, dtype=np.float64)
-        other = np.repeat(np.asarray(o_pose, dtype=np.float64)[None], k, 0)
-        d = o.epipolar_distance(np.arange(k), mine, np.full(k, k), other)          # (k, J, 2)
-        veto = False
-        total = 0
-        for v in range(k):
-            c = np.mean([(dis[0] * a[2] + dis[1] * b[2]) / 2 for dis, a, b in zip(d[v], mine[v], other[v])]) / self.threshold
-            total += c
-            if c > 1 and get_believe(o_pose) > 0.5:
-                veto = True
-        return total / k, veto
+        cost, veto = o.hypothesis_cost(np.arange(k), np.asarray(self.poses, dtype=np.float64), k,
+                                       np.asarray(o_pose, dtype=np.float64)[None])
+        return float(cost[0]), bool(veto[0])
 
     def get_3dpose_jf(self, init_threshold, lambda_t):
         """-> (cams, poses, pose3d, joints_views, ok) (src/tracking/hypothesis.py:23-44)."""

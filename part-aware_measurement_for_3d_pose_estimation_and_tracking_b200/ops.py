@@ -218,6 +218,28 @@ class GeometryOps:
             out = out[0]
         return out.cpu().numpy() if as_numpy else out
 
+    # -- a16 -------------------------------------------------------------------------------------
+    def mean_confidence(self, poses):
+        """Batched ``get_believe``: (B,J,3) -> (B,)."""
+        torch = _torch()
+        p = self._dev(np.asarray(poses, dtype=np.float64).reshape(-1, self.J, 3), torch.float64)
+        out = torch.empty(p.shape[0], dtype=torch.float64, device=self.dev)
+        self._call(self.lib.pam_mean_confidence, self._p(p), p.shape[0], self._p(out), self._stream())
+        return out.cpu().numpy()
+
+    def hypothesis_cost(self, hyp_cam, hyp_poses, other_cam: int, other_poses):
+        """``Hypothesis.calculate_cost`` of one hypothesis against B detections: -> (cost (B,), veto (B,))."""
+        torch = _torch()
+        hp = self._dev(np.asarray(hyp_poses, dtype=np.float64), torch.float64)
+        hc = self._dev(np.asarray(hyp_cam), torch.int32)
+        op = self._dev(np.asarray(other_poses, dtype=np.float64).reshape(-1, self.J, 3), torch.float64)
+        B = op.shape[0]
+        cost = torch.empty(B, dtype=torch.float64, device=self.dev)
+        veto = torch.empty(B, dtype=torch.uint8, device=self.dev)
+        self._call(self.lib.pam_hypothesis_cost, self._p(hp), self._p(hc), hp.shape[0], self._p(op), int(other_cam), B,
+                   self._p(cost), self._p(veto), self._stream())
+        return cost.cpu().numpy(), veto.cpu().numpy().astype(bool)
+
     # -- a9 --------------------------------------------------------------------------------------
     def ray_distance(self, camera: int, uv, points3d=None, want_dirs=False):
         """uv (n,2) as (u,v) -> (dist (n,) or None, dirs (n,3) or None)."""
@@ -240,7 +262,8 @@ _cache = {}
 
 
 def get_ops(cameras: Sequence, num_joints: int, params: Optional[dict] = None) -> GeometryOps:
-    key = (len(cameras), int(num_joints))
+    sig = tuple(sorted(params.items())) if isinstance(params, dict) else None
+    key = (len(cameras), int(num_joints), sig)
     ops = _cache.get(key)
     if ops is None:
         ops = GeometryOps(cameras, num_joints, params)
