@@ -197,6 +197,17 @@ def main():
     S, T = a.sequences, (a.frames or sh.T)
     V, J, D = sh.V, sh.J, sh.P
     MT = 8 if sh.P <= 6 else 12
+    # host-memory guard: every rank pins its detections and result buffers; never take more than half of
+    # this rank's share of the free host memory (an 8-rank run must not drive the box out of memory)
+    try:
+        import psutil
+        per_seq = T * (V * D * J * 3 * 4 + V * 4) + T * (MT * (J * 3 * 4 + 4) + 4) + T * sh.P * J * 3 * 8
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        budget = 0.5 * psutil.virtual_memory().available / max(1, local_world)
+        if S * per_seq > budget:
+            S = max(148, int(budget / per_seq) // 148 * 148)
+    except Exception:
+        pass
 
     # ---- synthetic input, generated straight into pinned host memory ---------------------------
     h_dets = torch.empty((S, T, V, D, J, 3), dtype=torch.float32, pin_memory=True)
@@ -219,6 +230,7 @@ def main():
     stream = torch.cuda.current_stream(dev)
     from pam_b200 import evaluate
     d_gt = torch.from_numpy(h_gt).to(dev) if do_eval else None
+    h_gt = None                                          # the ground truth lives on the device only
     pcp = torch.zeros((sh.P, 10, 2), dtype=torch.int64, device=dev)
     mpj = torch.zeros(2, dtype=torch.float64, device=dev)
 
