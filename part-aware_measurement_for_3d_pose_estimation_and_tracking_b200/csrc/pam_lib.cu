@@ -102,7 +102,7 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
     const float* gd = io.dets + (int64_t)s * io.seq_frames * nfl;
     const int* gc = io.counts + (int64_t)s * io.seq_frames * c.V;
     if (T > 0) stage_frame(dbuf, cbuf, gd, gc, nfl, c.V);
-    if (threadIdx.x == 0) carve(c, sh, arena);
+    if (threadIdx.x == 0) carve(c, sh, arena, g);
     __syncthreads();
     load_cameras(ctx, c, sh, cc);
     load_state(ctx, c, sh, g);
@@ -175,6 +175,7 @@ struct pam_handle {
     int device = 0;
     bool have_cameras = false;
     int track_threads = 128;
+    bool threads_forced = false;
     int track_minblocks = 0;   // 0 = choose per launch
     int num_sms = 148;
     int track_team = 0;        // 0 = choose per launch
@@ -248,7 +249,7 @@ int pam_create(const pam_config* cfg, int device, pam_handle** out) {
     const char* nt = getenv("PAM_TRACK_THREADS");
     if (nt) {
         int v = atoi(nt);
-        if (v >= 32 && v <= PAM_TRACK_THREADS_MAX) h->track_threads = (v / 32) * 32;
+        if (v >= 32 && v <= PAM_TRACK_THREADS_MAX) { h->track_threads = (v / 32) * 32; h->threads_forced = true; }
     } else {
         int want = cfg->max_tracks * cfg->num_joints;     // one thread per (track, joint)
         h->track_threads = want <= 64 ? 64 : (want <= 128 ? 128 : (want <= 192 ? 192 : 256));
@@ -257,7 +258,7 @@ int pam_create(const pam_config* cfg, int device, pam_handle** out) {
     const char* tm = getenv("PAM_TRACK_TEAM");
     if (tm) { int v = atoi(tm); if (v == 1 || v == 2) h->track_team = v; }
     const char* mb = getenv("PAM_TRACK_MINBLOCKS");
-    if (mb) { int v = atoi(mb); if (v == 4 || v == 6 || v == 8) h->track_minblocks = v; }
+    if (mb) { int v = atoi(mb); if (v == 4 || v == 6 || v == 8 || v == 10 || v == 12) h->track_minblocks = v; }
     *out = h;
     return PAM_OK;
 }
@@ -313,17 +314,26 @@ int pam_track_reset(pam_handle* h, void* d_state, int32_t S, void* stream) {
 typedef void (*track_kernel_t)(const DevCfg, const CamConst, char*, int, int, const TrackIO);
 
 // register budget variants: <= 128 threads with 4 / 6 / 8 CTAs per SM, or up to 256 threads
-static track_kernel_t pick_track_kernel(const pam_handle* h, int S) {
-    // few sequences: latency matters, take the full register budget; many: 6 CTAs per SM hide latency.
-    // Two lanes per (track, joint) (PAM_TRACK_TEAM=2) measured no faster than one on B200 (the phase is
-    // bound by the dependent FP64 chain of the solve, not by the work that can be split), so 1 is the default.
-    const bool many = S > 4 * h->num_sms;
-    const int mb = h->track_minblocks ? h->track_minblocks : (many ? 6 : 4);
+// Launch shape per call.  Few sequences: latency matters -- one CTA per sequence with the full register
+// budget.  Many sequences: the kernel is latency/barrier bound, so more, smaller CTAs per SM win
+// (measured on B200, Shelf shape: 128 thr x 4/SM 27 M frames/s, 128 x 6 33 M, 128 x 8 38 M, 64 x 12 40 M).
+// Two lanes per (track, joint) (PAM_TRACK_TEAM=2) measured no faster than one, so 1 is the default.
+static track_kernel_t pick_track_kernel(const pam_handle* h, int S, int* threads) {
+    const int per_sm = (S + h->num_sms - 1) / h->num_sms;
     const int team = h->track_team ? h->track_team : 1;
-    if (h->track_threads > 128) return team > 1 ? k_track_sequences<256, 2, 2> : k_track_sequences<256, 2, 1>;
+    int nt = h->track_threads;                       // PAM_TRACK_THREADS or the size-based default
+    int mb = h->track_minblocks;
+    if (!h->threads_forced && nt <= 128 && team == 1 && !mb && per_sm >= 10) nt = 64;
+    if (!mb) mb = nt > 128 ? (per_sm > 2 ? 4 : 2) : (nt <= 64 && per_sm >= 10 ? 12 : (per_sm >= 7 ? 8 : (per_sm > 4 ? 6 : 4)));
+    *threads = nt;
+    if (nt > 128) {
+        if (team > 1) return k_track_sequences<256, 2, 2>;
+        return mb >= 4 ? k_track_sequences<256, 4, 1> : k_track_sequences<256, 2, 1>;
+    }
     if (team > 1) return mb >= 6 ? k_track_sequences<128, 6, 2> : k_track_sequences<128, 4, 2>;
+    if (nt <= 64 && mb >= 10) return mb >= 12 ? k_track_sequences<64, 12, 1> : k_track_sequences<64, 10, 1>;
     switch (mb) {
-        case 8: return k_track_sequences<128, 8, 1>;
+        case 8: case 10: case 12: return k_track_sequences<128, 8, 1>;
         case 6: return k_track_sequences<128, 6, 1>;
         default: return k_track_sequences<128, 4, 1>;
     }
@@ -332,10 +342,11 @@ static track_kernel_t pick_track_kernel(const pam_handle* h, int S) {
 static int launch_track(pam_handle* h, void* d_state, int32_t S, int32_t T, int32_t frame0, const TrackIO& io,
                         cudaStream_t stream) {
     const size_t smem = track_smem_bytes(h->dc);
-    track_kernel_t kern = pick_track_kernel(h, S);
+    int threads = h->track_threads;
+    track_kernel_t kern = pick_track_kernel(h, S, &threads);
     if (smem + sizeof(SeqShared) > 48 * 1024)
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<S, h->track_threads, smem, stream>>>(h->dc, h->cc, (char*)d_state, T, frame0, io);
+    kern<<<S, threads, smem, stream>>>(h->dc, h->cc, (char*)d_state, T, frame0, io);
     h->launches += 1;
     CK(cudaGetLastError());
     return PAM_OK;

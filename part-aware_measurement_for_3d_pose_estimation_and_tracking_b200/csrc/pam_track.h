@@ -41,7 +41,7 @@ struct DevCfg {
     double conf_thr, epi_thr, joint_thr, alpha2d, lambda_a, veto_believe, fail_limit;
     float init_thr_f32;
     // per-sequence global state strides (bytes) -- see state_layout()
-    int64_t off_hdr, off_meta, off_view, off_hist, off_vel, off_nv, seq_bytes;
+    int64_t off_hdr, off_meta, off_view, off_hist, off_vel, off_nv, off_init, seq_bytes;
 };
 
 struct SeqHeader {
@@ -66,6 +66,8 @@ inline void state_layout(DevCfg& c) {
     c.off_view = take((int64_t)4 * c.max_trk * c.V * c.J * 3);
     c.off_vel = take((int64_t)4 * c.max_trk * c.J * 3);
     c.off_nv = take((int64_t)c.max_trk * c.J);
+    // scratch of the (rare) new-track initialisation: hyp_pose, hyp_cost (f64), hyp_veto, hyp_nvj (u8)
+    c.off_init = take((int64_t)8 * c.max_hyp * (c.J * 3 + c.D) + (int64_t)c.max_hyp * (c.D + c.J));
     c.seq_bytes = (o + 127) / 128 * 128;
 }
 
@@ -77,6 +79,7 @@ struct SeqGlobal {
     float* view;      // [max_trk][V][J][3]  (v, u, conf)
     float* vel;       // [max_trk][J][3]
     unsigned char* nv;  // [max_trk][J]
+    double* init;       // new-track initialisation scratch
     PAM_HD void bind(const DevCfg& c, char* base) {
         hdr = (SeqHeader*)(base + c.off_hdr);
         meta = (TrkMeta*)(base + c.off_meta);
@@ -84,6 +87,7 @@ struct SeqGlobal {
         view = (float*)(base + c.off_view);
         vel = (float*)(base + c.off_vel);
         nv = (unsigned char*)(base + c.off_nv);
+        init = (double*)(base + c.off_init);
     }
 };
 
@@ -126,7 +130,7 @@ struct SeqShared {
     int conflict[PAM_MAX_V];                 // camera needs the full assignment solver
     unsigned char nvj[PAM_MAX_TRK][PAM_MAX_J];
     // init
-    double believe[PAM_MAX_V][PAM_MAX_D];
+    double* believe;  // [V][D]               (arena) mean confidence of every detection
     unsigned char um_flag[PAM_MAX_V][PAM_MAX_D];
     signed char um[PAM_MAX_V][PAM_MAX_D];
     int um_n[PAM_MAX_V];
@@ -137,9 +141,9 @@ struct SeqShared {
     signed char hyp_det[PAM_MAX_HYP][PAM_MAX_V];
     unsigned char hyp_fail[PAM_MAX_HYP];
     signed char hyp_slot[PAM_MAX_HYP];
-    unsigned char* hyp_veto;   // [PAM_MAX_HYP][D]   (arena, aliases reproj)
-    unsigned char* hyp_nvj;    // [PAM_MAX_HYP][J]   (arena, aliases reproj)
-    double* hyp_cost;          // [PAM_MAX_HYP][D]   (arena, aliases reproj)
+    unsigned char* hyp_veto;   // [max_hyp][D]   (global scratch: initialisation is rare)
+    unsigned char* hyp_nvj;    // [max_hyp][J]   (global scratch)
+    double* hyp_cost;          // [max_hyp][D]   (global scratch)
     // output
     int out_n;
     signed char out_slot[PAM_MAX_TRK];
@@ -149,27 +153,18 @@ struct SeqShared {
 #endif
     // arena pointers (set by carve())
     double* aff;      // [V][max_trk][D]
-    double* reproj;   // [V][max_trk][J][2]   (v, u)
     double* raw;      // [max_trk][J][3]
-    double* hyp_pose; // [PAM_MAX_HYP][J][3]  (aliases reproj: phases do not overlap)
+    double* hyp_pose; // [max_hyp][J][3]      (global scratch)
 };
 
-// Arena layout (doubles): [camera constants][track meta][aff][union{reproj | init scratch}][raw]
+// Arena layout (doubles): [camera constants][track meta][aff][believe][raw]
 PAM_HD int64_t arena_cam_doubles(const DevCfg& c) { return (int64_t)c.V * (12 + 9 + 3) + (int64_t)c.V * c.V * 9; }
 PAM_HD int64_t arena_meta_doubles(const DevCfg& c) { return ((int64_t)sizeof(TrkMeta) * c.max_trk + 7) / 8; }
-PAM_HD int64_t arena_init_doubles(const DevCfg& c) {
-    // hyp_pose + hyp_cost + (hyp_veto, hyp_nvj bytes)
-    return (int64_t)c.max_hyp * c.J * 3 + (int64_t)c.max_hyp * c.D + ((int64_t)c.max_hyp * (c.D + c.J) + 7) / 8;
-}
-PAM_HD int64_t arena_union_doubles(const DevCfg& c) {
-    int64_t r = (int64_t)c.V * c.max_trk * c.J * 2, h = arena_init_doubles(c);
-    return r > h ? r : h;
-}
 PAM_HD int64_t arena_doubles(const DevCfg& c) {
-    return arena_cam_doubles(c) + arena_meta_doubles(c) + (int64_t)c.V * c.max_trk * c.D + arena_union_doubles(c) +
+    return arena_cam_doubles(c) + arena_meta_doubles(c) + (int64_t)c.V * c.max_trk * c.D + (int64_t)c.V * c.D +
            (int64_t)c.max_trk * c.J * 3;
 }
-PAM_HD void carve(const DevCfg& c, SeqShared& sh, double* arena) {
+PAM_HD void carve(const DevCfg& c, SeqShared& sh, double* arena, const SeqGlobal& g) {
     double* p = arena;
     sh.Vn = c.V;
     sh.P = p; p += (int64_t)c.V * 12;
@@ -178,13 +173,12 @@ PAM_HD void carve(const DevCfg& c, SeqShared& sh, double* arena) {
     sh.F = p; p += (int64_t)c.V * c.V * 9;
     sh.trk = (TrkMeta*)p; p += arena_meta_doubles(c);
     sh.aff = p; p += (int64_t)c.V * c.max_trk * c.D;
-    sh.reproj = p;
-    sh.hyp_pose = p;
-    sh.hyp_cost = p + (int64_t)c.max_hyp * c.J * 3;
+    sh.believe = p; p += (int64_t)c.V * c.D;
+    sh.raw = p;
+    sh.hyp_pose = g.init;
+    sh.hyp_cost = g.init + (int64_t)c.max_hyp * c.J * 3;
     sh.hyp_veto = (unsigned char*)(sh.hyp_cost + (int64_t)c.max_hyp * c.D);
     sh.hyp_nvj = sh.hyp_veto + (int64_t)c.max_hyp * c.D;
-    p += arena_union_doubles(c);
-    sh.raw = p;
 }
 
 struct HostCtx {
@@ -413,7 +407,7 @@ PAM_HD double hyp_cost(const DevCfg& c, const SeqShared& sh, const float* dets, 
         }
         double pc = acc.total() / (double)J / c.epi_thr;
         total += pc;
-        if (pc > 1.0 && sh.believe[c2][d2] > c.veto_believe) veto = true;
+        if (pc > 1.0 && sh.believe[c2 * c.D + d2] > c.veto_believe) veto = true;
     }
     return total / (double)nvw;
 }
@@ -446,8 +440,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
     }
     const int n = sh.hdr.ntracks;
 
-    // ---- phase 1: ageing + snapshot (IterativeTracker.py:126-129) and reprojection of every track
-    //      joint into every camera (ivclabpose.py:91-98) ------------------------------------------
+    // ---- phase 1: ageing + snapshot (IterativeTracker.py:126-129) ---------------------------------
     PAM_FOR(i, n) {
         TrkMeta& t = sh.trk[sh.hdr.order[i]];
         t.already = 0; t.age += 1; t.tsu += 1;
@@ -472,25 +465,6 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
     }
     PAM_FOR(i, PAM_MAX_V * PAM_MAX_TRK / 4) ((int*)sh.t2d)[i] = -1;
     PAM_FOR(i, PAM_MAX_V * PAM_MAX_D / 4) ((int*)sh.d2t)[i] = -1;
-    PAM_FOR(it, n * J) {
-        const int i = fast_div(it, c.inv_J), j = it - i * J;
-        const int s = sh.hdr.order[i];
-        const TrkMeta& t = sh.trk[s];
-        const int last = (t.hist_start + t.hist_len - 1) % PAM_HIST;     // hist fields are stable here
-        const double* X = g.hist + ((int64_t)(s * PAM_HIST + last) * J + j) * 3;
-        const double x = X[0], y = X[1], z = X[2];
-        PAM_NOUNROLL for (int cam = 0; cam < V; ++cam) {
-            if (counts[cam] <= 0) continue;
-            const double* P = sh.Pc(cam);
-            double a = P[0] * x + P[1] * y + P[2] * z + P[3];
-            double b = P[4] * x + P[5] * y + P[6] * z + P[7];
-            double w = P[8] * x + P[9] * y + P[10] * z + P[11];
-            double* r = sh.reproj + ((int64_t)(cam * MT + i) * J + j) * 2;
-            const double iw = rcp_f64(w);
-            r[0] = b * iw;   // v
-            r[1] = a * iw;   // u
-        }
-    }
     ctx.sync();
     PAM_MARK(0);
 
@@ -498,14 +472,21 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
     PAM_FOR(it, V * n * D) {
         const int i = fast_div(it, c.inv_VD), rem = it - i * (V * D), cam = fast_div(rem, c.inv_D), d = rem - cam * D;
         if (d >= sh.m[cam]) continue;
-        const double* r = sh.reproj + (int64_t)(cam * MT + i) * J * 2;
+        // reprojection of the track's last pose into this camera (ivclabpose.py:91-98), recomputed per
+        // detection: cheaper than staging V x n x J pixel pairs in shared memory (9 KB less per CTA)
+        const double* X = g.hist + (int64_t)(sh.hdr.order[i] * PAM_HIST + sh.last[i]) * J3;
+        const double* P = sh.Pc(cam);
+        const double p0 = P[0], p1 = P[1], p2 = P[2], p3 = P[3], p4 = P[4], p5 = P[5], p6 = P[6], p7 = P[7];
+        const double p8 = P[8], p9 = P[9], p10 = P[10], p11 = P[11];
         const float* q = dets + (int64_t)(cam * D + d) * J3;
         const double inv_denom = sh.inv_denom[i];
         double sum = 0.0;
         int cnt = 0;
         PAM_NOUNROLL for (int j = 0; j < J; ++j) {
-            double dv = r[j * 2 + 0] - (double)q[j * 3 + 0];
-            double du = r[j * 2 + 1] - (double)q[j * 3 + 1];
+            const double x = X[j * 3], y = X[j * 3 + 1], z = X[j * 3 + 2];
+            const double iw = rcp_f64(p8 * x + p9 * y + p10 * z + p11);
+            const double dv = (p4 * x + p5 * y + p6 * z + p7) * iw - (double)q[j * 3 + 0];
+            const double du = (p0 * x + p1 * y + p2 * z + p3) * iw - (double)q[j * 3 + 1];
             double cj = 1.0 - sqrt_f64(dv * dv + du * du) * inv_denom;
             if (cj > 0.0) { sum += cj; ++cnt; }
         }
@@ -593,7 +574,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         PAM_NOUNROLL for (int j = 0; j < J; ++j)
             if (q[j * 3 + 2] >= 0.0f) kept[nk++] = (double)q[j * 3 + 2];
         double b = np_sum(kept, nk) / (double)nk;   // 0/0 -> NaN like np.mean([])
-        sh.believe[cam][d] = b;
+        sh.believe[cam * D + d] = b;
         sh.um_flag[cam][d] = (i < 0 && b > c.conf_thr) ? 1 : 0;
     }
     ctx.sync();

@@ -30,9 +30,9 @@ extern "C" int hostemu_track_sequences(const pam_config* cfg, const float* P, co
     const int64_t fstride = (int64_t)c.V * c.D * c.J * 3;
     for (int s = 0; s < S; ++s) {
         std::memset((void*)sh, 0, sizeof(SeqShared));
-        carve(c, *sh, arena.data());
         SeqGlobal g;
         g.bind(c, state + (int64_t)s * c.seq_bytes);
+        carve(c, *sh, arena.data(), g);
         load_cameras(ctx, c, *sh, cc);
         load_state(ctx, c, *sh, g);
         for (int t = 0; t < T; ++t) {
