@@ -100,6 +100,13 @@ struct FrameOut {
     int* assoc;            // [V][D]  track id matched to each detection, -1 = unmatched
 };
 
+// One usable view of a track for the current frame: where its (v, u, conf) triples live (the staged
+// detections for a view matched this frame, the persisted copy in HBM for a stale one), its camera and age.
+struct ViewSrc {
+    const float* p;
+    int cid, T;
+};
+
 // Block-shared working set.  Fixed-size part; the J-dependent arrays live in `arena`.
 struct SeqShared {
     SeqHeader hdr;
@@ -123,7 +130,7 @@ struct SeqShared {
     signed char t2d[PAM_MAX_V][PAM_MAX_TRK];
     signed char d2t[PAM_MAX_V][PAM_MAX_D];
     signed char vk[PAM_MAX_V][PAM_MAX_TRK];  // view slot written by add_pose
-    signed char gv_idx[PAM_MAX_TRK][PAM_MAX_V];
+    ViewSrc* vsrc;    // [max_trk][V]         (arena) gathered views per track, dict order
     int gv_n[PAM_MAX_TRK];
     int do_update[PAM_MAX_TRK];
     int fail[PAM_MAX_TRK];                   // joints left with < 2 views
@@ -162,7 +169,7 @@ PAM_HD int64_t arena_cam_doubles(const DevCfg& c) { return (int64_t)c.V * (12 + 
 PAM_HD int64_t arena_meta_doubles(const DevCfg& c) { return ((int64_t)sizeof(TrkMeta) * c.max_trk + 7) / 8; }
 PAM_HD int64_t arena_doubles(const DevCfg& c) {
     return arena_cam_doubles(c) + arena_meta_doubles(c) + (int64_t)c.V * c.max_trk * c.D + (int64_t)c.V * c.D +
-           (int64_t)c.max_trk * c.J * 3;
+           (int64_t)c.max_trk * c.J * 3 + (int64_t)c.max_trk * c.V * 2;
 }
 PAM_HD void carve(const DevCfg& c, SeqShared& sh, double* arena, const SeqGlobal& g) {
     double* p = arena;
@@ -174,7 +181,8 @@ PAM_HD void carve(const DevCfg& c, SeqShared& sh, double* arena, const SeqGlobal
     sh.trk = (TrkMeta*)p; p += arena_meta_doubles(c);
     sh.aff = p; p += (int64_t)c.V * c.max_trk * c.D;
     sh.believe = p; p += (int64_t)c.V * c.D;
-    sh.raw = p;
+    sh.raw = p; p += (int64_t)c.max_trk * c.J * 3;
+    sh.vsrc = (ViewSrc*)p;
     sh.hyp_pose = g.init;
     sh.hyp_cost = g.init + (int64_t)c.max_hyp * c.J * 3;
     sh.hyp_veto = (unsigned char*)(sh.hyp_cost + (int64_t)c.max_hyp * c.D);
@@ -281,9 +289,34 @@ PAM_HD void store_state(Ctx& ctx, const DevCfg& c, const SeqShared& sh, const Se
 // Weighted DLT over the surviving views (bit a of `alive`); T == nullptr means all ages 0.
 // Fresh-only systems go through the Gram/Cholesky fold; if that is judged too close to singular
 // (or any view is stale) the rows are folded again with Givens rotations.
-template <class Team, class CidT>
-PAM_HD void dlt_from_views(const Team& tm, const DevCfg& c, const SeqShared& sh, int Vt, const CidT* cid, const int* T,
-                           const double* u, const double* v, uint32_t alive, double* X) {
+// View accessors: the update path reads (u, v) of joint j straight from the ViewSrc records in shared
+// memory (no per-thread copies: with ~800 resident threads per SM thread-local arrays would spill to
+// L2/HBM); the rare init path passes small local arrays.
+struct SrcViews {
+    const ViewSrc* vs;
+    int j3;
+    const double* w_age;
+    PAM_HD int cid(int a) const { return vs[a].cid; }
+    PAM_HD double u(int a) const { return (double)vs[a].p[j3 + 1]; }
+    PAM_HD double v(int a) const { return (double)vs[a].p[j3]; }
+    PAM_HD double w(int a) const { return w_age[vs[a].T]; }
+    PAM_HD int age(int a) const { return vs[a].T; }
+};
+struct ArrayViews {
+    const signed char* c;
+    const double* uu;
+    const double* vv;
+    double w0;
+    PAM_HD int cid(int a) const { return c[a]; }
+    PAM_HD double u(int a) const { return uu[a]; }
+    PAM_HD double v(int a) const { return vv[a]; }
+    PAM_HD double w(int) const { return w0; }
+    PAM_HD int age(int) const { return 0; }
+};
+
+// Weighted DLT over the surviving views (bit a of `alive`).
+template <class Team, class Views>
+PAM_HD void dlt_from_views(const Team& tm, const SeqShared& sh, int Vt, const Views& vw, uint32_t alive, double* X) {
     // Gram / Cholesky fold first, stale views included with their weights e^{-lambda_t T}: as long as
     // the Cholesky pivots stay above 1e-6 of the diagonal (two fresh views, or one fresh view plus views
     // one frame old) the squared system resolves the solution to < 1e-10 relative.  Otherwise -- only
@@ -293,7 +326,7 @@ PAM_HD void dlt_from_views(const Team& tm, const DevCfg& c, const SeqShared& sh,
     int path = -1;
     acc.reset(true);
     PAM_NOUNROLL for (int a = tm.rank; a < Vt; a += Team::size)
-        if ((alive >> a) & 1u) acc.add_view(sh.Pc(cid[a]), u[a], v[a], c.w_age[T ? T[a] : 0]);
+        if ((alive >> a) & 1u) acc.add_view(sh.Pc(vw.cid(a)), vw.u(a), vw.v(a), vw.w(a));
     if (Team::size > 1) {     // the Gram matrix is additive over views
         acc.r00 = tm.sum_f64(acc.r00); acc.r01 = tm.sum_f64(acc.r01); acc.r02 = tm.sum_f64(acc.r02);
         acc.r03 = tm.sum_f64(acc.r03); acc.r11 = tm.sum_f64(acc.r11); acc.r12 = tm.sum_f64(acc.r12);
@@ -304,7 +337,7 @@ PAM_HD void dlt_from_views(const Team& tm, const DevCfg& c, const SeqShared& sh,
     if (path < 0) {
         acc.reset(false);
         PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
-            if ((alive >> a) & 1u) acc.add_view(sh.Pc(cid[a]), u[a], v[a], c.w_age[T ? T[a] : 0]);
+            if ((alive >> a) & 1u) acc.add_view(sh.Pc(vw.cid(a)), vw.u(a), vw.v(a), vw.w(a));
         acc.solve(X, &path);
     }
 }
@@ -313,36 +346,37 @@ PAM_HD void dlt_from_views(const Team& tm, const DevCfg& c, const SeqShared& sh,
 //   views 0..Vt-1 in the track's dict order; cid/T per view; (u, v) per view; next = predicted joint.
 // Returns the number of surviving views; X = triangulated joint (or `next` when < 2 views).
 template <class Team>
-PAM_HD int joint_update(const Team& tm, const DevCfg& c, const SeqShared& sh, int Vt, const int* cid, const int* T,
-                        const double* u, const double* v, const double* next, double* X) {
-    uint32_t conflict[PAM_MAX_V];
-    PAM_NOUNROLL for (int a = 0; a < Vt; ++a) conflict[a] = 0u;
+PAM_HD int joint_update(const Team& tm, const DevCfg& c, const SeqShared& sh, int Vt, const SrcViews& vw,
+                        const double* next, double* X) {
+    // conflict bit (a * 8 + b) for a < b: the pair's symmetric epipolar distance exceeds the threshold
+    uint64_t conflict = 0ull;
     int k = 0;
-    PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
+    PAM_NOUNROLL for (int a = 0; a < Vt; ++a) {
+        const double ua = vw.u(a), va = vw.v(a);
+        const int ca = vw.cid(a);
         PAM_NOUNROLL for (int b = a + 1; b < Vt; ++b, ++k) {
             if (Team::size > 1 && (k & (Team::size - 1)) != tm.rank) continue;   // view pairs are dealt round-robin
-            double dab = epi_dist_f64(sh.Fc(cid[a], cid[b]), u[a], v[a], u[b], v[b]);
-            double dba = epi_dist_f64(sh.Fc(cid[b], cid[a]), u[b], v[b], u[a], v[a]);
-            double D = (dab + dba) / 2.0;
-            double A = 1.0 - D * c.inv_joint_thr;
-            if (A < 0.0) conflict[a] |= (1u << b);
+            const double ub = vw.u(b), vb = vw.v(b);
+            const int cb = vw.cid(b);
+            const double dab = epi_dist_f64(sh.Fc(ca, cb), ua, va, ub, vb);
+            const double dba = epi_dist_f64(sh.Fc(cb, ca), ub, vb, ua, va);
+            const double A = 1.0 - (dab + dba) / 2.0 * c.inv_joint_thr;
+            if (A < 0.0) conflict |= 1ull << (a * 8 + b);
         }
-    uint32_t any = 0u;
-    PAM_NOUNROLL for (int a = 0; a < Vt; ++a) {
-        conflict[a] = tm.or_u32(conflict[a]);
-        any |= conflict[a];
     }
-    uint32_t alive = (Vt >= 32) ? 0xffffffffu : ((1u << Vt) - 1u);
-    if (any) {                     // identical on every lane of the team
-        double rd[PAM_MAX_V];
-        PAM_NOUNROLL for (int a = 0; a < Vt; ++a) rd[a] = 0.0;
-        PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
+    if (Team::size > 1) {
+        const uint32_t lo = tm.or_u32((uint32_t)conflict), hi = tm.or_u32((uint32_t)(conflict >> 32));
+        conflict = ((uint64_t)hi << 32) | lo;
+    }
+    uint32_t alive = (1u << Vt) - 1u;
+    if (conflict) {                // identical on every lane of the team; rare, so the ray distances are
+        PAM_NOUNROLL for (int a = 0; a < Vt; ++a)                     // simply recomputed per conflict
             PAM_NOUNROLL for (int b = a + 1; b < Vt; ++b) {
-                if (!((conflict[a] >> b) & 1u)) continue;
+                if (!((conflict >> (a * 8 + b)) & 1ull)) continue;
                 if (!((alive >> a) & 1u) || !((alive >> b) & 1u)) continue;
-                if (rd[a] == 0.0) rd[a] = ray_point_distance(sh.RKc(cid[a]), sh.posc(cid[a]), u[a], v[a], next);
-                if (rd[b] == 0.0) rd[b] = ray_point_distance(sh.RKc(cid[b]), sh.posc(cid[b]), u[b], v[b], next);
-                if (rd[a] > rd[b]) alive &= ~(1u << a); else alive &= ~(1u << b);
+                const double ra = ray_point_distance(sh.RKc(vw.cid(a)), sh.posc(vw.cid(a)), vw.u(a), vw.v(a), next);
+                const double rb = ray_point_distance(sh.RKc(vw.cid(b)), sh.posc(vw.cid(b)), vw.u(b), vw.v(b), next);
+                if (ra > rb) alive &= ~(1u << a); else alive &= ~(1u << b);
             }
     }
     const int nv = popcount32(alive);
@@ -350,7 +384,7 @@ PAM_HD int joint_update(const Team& tm, const DevCfg& c, const SeqShared& sh, in
         X[0] = next[0]; X[1] = next[1]; X[2] = next[2];
         return nv;
     }
-    dlt_from_views(tm, c, sh, Vt, cid, T, u, v, alive, X);
+    dlt_from_views(tm, sh, Vt, vw, alive, X);
     return nv;
 }
 
@@ -382,7 +416,7 @@ PAM_HD int joint_init(const DevCfg& c, const SeqShared& sh, int Vt, const signed
     }
     const int nv = popcount32(alive);
     if (nv < 2) return nv;
-    dlt_from_views(SoloTeam(), c, sh, Vt, cid, (const int*)nullptr, u, v, alive, X);
+    dlt_from_views(SoloTeam(), sh, Vt, ArrayViews{cid, u, v, c.w_age[0]}, alive, X);
     return nv;
 }
 
@@ -556,9 +590,19 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             sh.vk[cam][i] = (signed char)k;
         }
         int cnt = 0;
-        if (t.already)
-            PAM_NOUNROLL for (int k = 0; k < t.nviews; ++k)
-                if (frame - t.view_time[k] <= c.stale_window) sh.gv_idx[i][cnt++] = (signed char)k;
+        if (t.already) {
+            const int s = sh.hdr.order[i];
+            PAM_NOUNROLL for (int k = 0; k < t.nviews; ++k) {
+                const int age = frame - t.view_time[k];
+                if (age > c.stale_window) continue;
+                const int cam = t.view_cid[k];
+                ViewSrc& vs = sh.vsrc[i * V + cnt++];
+                vs.cid = cam;
+                vs.T = age;
+                // a view matched this frame is read straight from the staged detections
+                vs.p = (age == 0) ? dets + (int64_t)(cam * D + sh.t2d[cam][i]) * J3 : g.view + (int64_t)(s * V + k) * J3;
+            }
+        }
         sh.gv_n[i] = cnt;
         sh.do_update[i] = (t.already && cnt >= 2) ? 1 : 0;
     }
@@ -569,11 +613,13 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         if (out.assoc) out.assoc[it] = (i >= 0) ? sh.trk[sh.hdr.order[i]].track_id : -1;
         if (d >= sh.m[cam]) continue;
         const float* q = dets + (int64_t)(cam * D + d) * J3;
-        double kept[PAM_MAX_J];
         int nk = 0;
+        PAM_NOUNROLL for (int j = 0; j < J; ++j) nk += (q[j * 3 + 2] >= 0.0f) ? 1 : 0;
+        NpSumStream<double> acc;                  // numpy's summation order without a scratch array
+        acc.begin(nk);
         PAM_NOUNROLL for (int j = 0; j < J; ++j)
-            if (q[j * 3 + 2] >= 0.0f) kept[nk++] = (double)q[j * 3 + 2];
-        double b = np_sum(kept, nk) / (double)nk;   // 0/0 -> NaN like np.mean([])
+            if (q[j * 3 + 2] >= 0.0f) acc.push((double)q[j * 3 + 2]);
+        double b = acc.total() / (double)nk;      // 0/0 -> NaN like np.mean([])
         sh.believe[cam * D + d] = b;
         sh.um_flag[cam][d] = (i < 0 && b > c.conf_thr) ? 1 : 0;
     }
@@ -595,22 +641,9 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             const float fdt = (float)sh.dt[i];
             double next[3];
             for (int k = 0; k < 3; ++k) next[k] = Xl[k] + (double)(vel[k] * fdt);
-            int cid[PAM_MAX_V], T[PAM_MAX_V];
-            double u[PAM_MAX_V], v[PAM_MAX_V];
             const int Vt = sh.gv_n[i];
-            PAM_NOUNROLL for (int a = 0; a < Vt; ++a) {
-                const int k = sh.gv_idx[i][a];
-                const int cam = t.view_cid[k];
-                cid[a] = cam;
-                T[a] = frame - t.view_time[k];
-                // a view matched this frame is read straight from the staged detections
-                const float* q = (T[a] == 0) ? dets + ((int64_t)(cam * D + sh.t2d[cam][i]) * J + j) * 3
-                                             : g.view + ((int64_t)(s * V + k) * J + j) * 3;
-                v[a] = (double)q[0];
-                u[a] = (double)q[1];
-            }
             double X[3];
-            const int nv = joint_update(tm, c, sh, Vt, cid, T, u, v, next, X);
+            const int nv = joint_update(tm, c, sh, Vt, SrcViews{sh.vsrc + i * V, j * 3, c.w_age}, next, X);
             if (tm.rank == 0) {
                 sh.nvj[i][j] = (unsigned char)nv;
                 if (nv < 2) ctx.atomic_inc(&sh.fail[i]);
