@@ -635,7 +635,6 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             const int i = fast_div(it, c.inv_J), j = it - i * J;
             if (!sh.do_update[i]) continue;          // uniform within a team
             const int s = sh.hdr.order[i];
-            const TrkMeta& t = sh.trk[s];
             const double* Xl = g.hist + ((int64_t)(s * PAM_HIST + sh.last[i]) * J + j) * 3;
             const float* vel = g.vel + (int64_t)(s * J + j) * 3;
             const float fdt = (float)sh.dt[i];
