@@ -304,6 +304,38 @@ def main():
     if rank != 0:
         return
 
+    # ---- BASELINE.json configs[1] taken literally: ONE stream of T frames (frame-serial latency) ----
+    single = None
+    try:
+        t1 = tracker.SequenceTracker(cams, synth.tracker_params(a.shape), 1, max_detections=D, max_tracks=MT,
+                                     arm_joints=sh.arm_joints, device=local_rank)
+        d1, c1 = d_dets[:1].contiguous(), d_counts[:1].contiguous()
+        o1 = t1.alloc_outputs(T, nviews=False, assoc=False)
+        best = 1e30
+        for it in range(4):
+            t1.restart()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            t1.run(d1, c1, out=o1, frame0=0)
+            s1.record(stream)
+            torch.cuda.synchronize(dev)
+            if it:
+                best = min(best, s0.elapsed_time(s1))
+        t1.check()
+        hd1, hc1 = h_dets[:1].numpy(), h_counts[:1].numpy()
+        ho1 = dict(count=np.empty((1, T), np.int32), ids=np.empty((1, T, MT), np.int32),
+                   joints=np.empty((1, T, MT, J, 3), np.float32), nviews=None, assoc=None)
+        t1.run_host(hd1, hc1, fresh=True, nviews=False, out=ho1)
+        w0 = time.perf_counter()
+        for _ in range(3):
+            t1.run_host(hd1, hc1, fresh=True, nviews=False, out=ho1)
+        wall = (time.perf_counter() - w0) / 3
+        single = {"workload": f"one {a.shape} stream of {T} frames on one CTA", "value": T / (best * 1e-3),
+                  "unit": "frames/s", "us_per_frame": best * 1e3 / T, "e2e_value": T / wall}
+        t1.close()
+    except Exception as e:       # the headline numbers above must not depend on this extra
+        single = {"error": str(e)[:200]}
+
     # ---- roofline of the tracker kernel ----------------------------------------------------------
     peaks = {}
     try:
@@ -345,6 +377,7 @@ def main():
                    "mpjpe_mm": (round(counters[4].item() / max(1, counters[5].item()) / 1e3, 3) if do_eval else None),
                    "threads_per_cta": int(os.environ.get("PAM_TRACK_THREADS", "0")) or "auto"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "single_stream": single,
     }
     print(json.dumps(line))
 
