@@ -81,7 +81,8 @@ typedef struct pam_state_layout {
     int64_t off_vel;            /* float  [slot][J][3]            velocity                          */
     int64_t off_nviews;         /* uint8  [slot][J]               views used for the last pose      */
     int32_t meta_ints;          /* ints per slot: id,hits,age,tsu,state,already,nviews,hist_start,
-                                   hist_len, view_cid[8], view_time[8], hist_time[hist_ring]       */
+                                   hist_len, view_cid[8], view_time[8], hist_time[hist_ring],
+                                   then 8 bytes camera -> view-slot map                          */
     int32_t hist_ring;          /* ring length                                                      */
     int32_t max_views;          /* 8                                                                */
     int32_t max_order;          /* 16                                                               */

@@ -107,6 +107,37 @@ struct NpSumStream {
     PAM_HD T total() const { return res; }
 };
 
+// get_believe (utils/calculate.py:8-14): mean of the confidences that are >= 0, summed in numpy's
+// order.  q = (v, u, conf) triples of one detection.  Common case (no negative confidence): one strided
+// pass; otherwise the selected values are streamed through the same accumulator pattern.
+PAM_HD double mean_confidence(const float* q, int J) {
+    int nk = 0;
+    PAM_NOUNROLL for (int j = 0; j < J; ++j) nk += (q[j * 3 + 2] >= 0.0f) ? 1 : 0;
+    if (nk == J) {
+        double res;
+        if (J < 8) {
+            res = 0.0;
+            PAM_NOUNROLL for (int j = 0; j < J; ++j) res += (double)q[j * 3 + 2];
+        } else {
+            double r0 = q[2], r1 = q[5], r2 = q[8], r3 = q[11], r4 = q[14], r5 = q[17], r6 = q[20], r7 = q[23];
+            int i = 8;
+            PAM_NOUNROLL for (; i < J - (J % 8); i += 8) {
+                const float* p = q + i * 3 + 2;
+                r0 += (double)p[0]; r1 += (double)p[3]; r2 += (double)p[6]; r3 += (double)p[9];
+                r4 += (double)p[12]; r5 += (double)p[15]; r6 += (double)p[18]; r7 += (double)p[21];
+            }
+            res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+            PAM_NOUNROLL for (; i < J; ++i) res += (double)q[i * 3 + 2];
+        }
+        return res / (double)J;
+    }
+    NpSumStream<double> acc;
+    acc.begin(nk);
+    PAM_NOUNROLL for (int j = 0; j < J; ++j)
+        if (q[j * 3 + 2] >= 0.0f) acc.push((double)q[j * 3 + 2]);
+    return acc.total() / (double)nk;              // 0/0 -> NaN like np.mean([])
+}
+
 // ------------------------------------------------------------------------------------------
 // epipolar geometry
 // ------------------------------------------------------------------------------------------

@@ -55,6 +55,7 @@ struct TrkMeta {
     int view_cid[PAM_MAX_V];
     int view_time[PAM_MAX_V];
     int hist_time[PAM_HIST];
+    signed char view_slot[PAM_MAX_V];   // camera -> position in the view list (dict key lookup), -1 = absent
 };
 
 inline void state_layout(DevCfg& c) {
@@ -582,9 +583,8 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         TrkMeta& t = sh.trk[sh.hdr.order[i]];
         PAM_NOUNROLL for (int cam = 0; cam < V; ++cam) {
             if (sh.t2d[cam][i] < 0) continue;
-            int k = 0;
-            PAM_NOUNROLL while (k < t.nviews && t.view_cid[k] != cam) ++k;
-            if (k == t.nviews) { t.nviews = k + 1; t.view_cid[k] = cam; }
+            int k = t.view_slot[cam];                 // view slot of this camera, -1 = not in the dict yet
+            if (k < 0) { k = t.nviews++; t.view_cid[k] = cam; t.view_slot[cam] = (signed char)k; }
             t.view_time[k] = frame;
             t.already = 1;
             sh.vk[cam][i] = (signed char)k;
@@ -613,13 +613,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         if (out.assoc) out.assoc[it] = (i >= 0) ? sh.trk[sh.hdr.order[i]].track_id : -1;
         if (d >= sh.m[cam]) continue;
         const float* q = dets + (int64_t)(cam * D + d) * J3;
-        int nk = 0;
-        PAM_NOUNROLL for (int j = 0; j < J; ++j) nk += (q[j * 3 + 2] >= 0.0f) ? 1 : 0;
-        NpSumStream<double> acc;                  // numpy's summation order without a scratch array
-        acc.begin(nk);
-        PAM_NOUNROLL for (int j = 0; j < J; ++j)
-            if (q[j * 3 + 2] >= 0.0f) acc.push((double)q[j * 3 + 2]);
-        double b = acc.total() / (double)nk;      // 0/0 -> NaN like np.mean([])
+        const double b = mean_confidence(q, J);
         sh.believe[cam * D + d] = b;
         sh.um_flag[cam][d] = (i < 0 && b > c.conf_thr) ? 1 : 0;
     }
@@ -855,7 +849,10 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
                 t.track_id = sh.hdr.next_id++;
                 t.hits = 1; t.age = 1; t.tsu = 0; t.state = ST_TENTATIVE; t.already = 0;
                 t.nviews = sh.hyp_nviews[h];
-                PAM_NOUNROLL for (int k = 0; k < t.nviews; ++k) { t.view_cid[k] = sh.hyp_cam[h][k]; t.view_time[k] = frame; }
+                PAM_NOUNROLL for (int cc2 = 0; cc2 < PAM_MAX_V; ++cc2) t.view_slot[cc2] = -1;
+                PAM_NOUNROLL for (int k = 0; k < t.nviews; ++k) {
+                    t.view_cid[k] = sh.hyp_cam[h][k]; t.view_time[k] = frame; t.view_slot[sh.hyp_cam[h][k]] = (signed char)k;
+                }
                 t.hist_start = 0; t.hist_len = 1; t.hist_time[0] = frame;
                 sh.hyp_slot[h] = (signed char)s;
             }
