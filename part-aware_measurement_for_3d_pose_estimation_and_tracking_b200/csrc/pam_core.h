@@ -33,8 +33,10 @@
 // run-time trip counts are kept rolled.
 #if defined(__CUDACC__)
 #define PAM_NOUNROLL _Pragma("unroll 1")
+#define PAM_UNROLL2 _Pragma("unroll 2")
 #else
 #define PAM_NOUNROLL
+#define PAM_UNROLL2
 #endif
 
 #define PAM_MAX_V 8        // cameras per rig handled by the stateful tracker

@@ -517,7 +517,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         const double inv_denom = sh.inv_denom[i];
         double sum = 0.0;
         int cnt = 0;
-        PAM_NOUNROLL for (int j = 0; j < J; ++j) {
+        PAM_UNROLL2 for (int j = 0; j < J; ++j) {     // two joints in flight: the chain per joint is ~20 deep
             const double x = X[j * 3], y = X[j * 3 + 1], z = X[j * 3 + 2];
             const double iw = rcp_f64(p8 * x + p9 * y + p10 * z + p11);
             const double dv = (p4 * x + p5 * y + p6 * z + p7) * iw - (double)q[j * 3 + 0];
