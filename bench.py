@@ -76,6 +76,24 @@ def generate(shape, seq_ids, T, dets_out, counts_out, gt_out=None, workers=None)
     return rig
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this rank to the CPUs next to its GPU (NVML's ideal CPU affinity) BEFORE the pinned host
+    buffers are allocated, so that first-touch places them on the GPU's NUMA node: on a two-socket 8-GPU
+    box the H2D/D2H legs of `e2e` otherwise cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [i * 64 + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -193,6 +211,7 @@ def main():
     rank, local_rank, world = pdist.init()
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     sh = synth.SHAPES[a.shape]
     S, T = a.sequences, (a.frames or sh.T)
     V, J, D = sh.V, sh.J, sh.P
@@ -372,7 +391,7 @@ def main():
         "config": {"workload": f"{a.shape}: {V} cameras x {sh.P} people x {J} joints x {T} frames, {S} independent "
                                f"sequences per GPU", "sequences_per_gpu": S, "frames": T, "max_tracks": MT,
                    "l2": f"inputs larger than L2 ({d_dets.numel() * 4 / 1e9:.2f} GB of detections per GPU per step)",
-                   "gen_seconds": round(gen_s, 1), "reports_per_step": int(counters[0].item()),
+                   "gen_seconds": round(gen_s, 1), "cpus_bound_per_rank": numa_cpus, "reports_per_step": int(counters[0].item()),
                    "pcp_percent": (round(100.0 * counters[2].item() / max(1, counters[3].item()), 3) if do_eval else None),
                    "mpjpe_mm": (round(counters[4].item() / max(1, counters[5].item()) / 1e3, 3) if do_eval else None),
                    "threads_per_cta": int(os.environ.get("PAM_TRACK_THREADS", "0")) or "auto"},
