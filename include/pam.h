@@ -216,6 +216,16 @@ int pam_eval_pcp(pam_handle* h, const int32_t* d_out_count, const float* d_out_j
                  int32_t frame_begin, int32_t frame_end, double alpha, uint64_t* d_counters, double* d_mpjpe,
                  void* stream);
 
+/* Matching step of EvaluatePanoptic.evaluate (evalmodel.py:291-320): for every predicted pose of every
+ * frame the MPJPE (mm, visible joints) to its closest ground-truth body.  d_out_count / d_out_joints:
+ * tracker outputs (J = 17 COCO or 19 COCO-19); d_gt_mm [S][T][max_gt][14][3] f64 in millimetres,
+ * d_gt_vis [S][T][max_gt][14] u8, d_n_gt [S][T] i32 -> d_mpjpe [S][T][max_tracks] f64, d_gt_index
+ * [S][T][max_tracks] i32 (-1: no ground truth in the frame / slot unused).  AP, recall and MPJPE are
+ * then list reductions on the host (pam_b200.evaluate.panoptic_metrics). */
+int pam_eval_panoptic_match(pam_handle* h, const int32_t* d_out_count, const float* d_out_joints, const double* d_gt_mm,
+                            const uint8_t* d_gt_vis, const int32_t* d_n_gt, int32_t S, int32_t T, int32_t max_gt,
+                            int32_t max_tracks, double* d_mpjpe, int32_t* d_gt_index, void* stream);
+
 /* number of kernel launches issued through this handle so far (bench.py "gpu_launches") */
 int64_t pam_launch_count(const pam_handle* h);
 

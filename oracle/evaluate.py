@@ -84,3 +84,64 @@ def pcp_table(counters):
         out["Total"] = c[:, :, 0].sum(1) / c[:, :, 1].sum(1)
         out["total_avg"] = c[:, :, 0].sum() / c[:, :, 1].sum()
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Panoptic evaluation (src/evalmodel.py:208-350), on arrays instead of json / pickle files
+# ------------------------------------------------------------------------------------------------
+def panoptic_eval_list(preds, gts):
+    """``preds[t]`` = (n, 3, 17) predictions in metres (the pickle's arrays), ``gts[t]`` = dict with
+    'joints_3d' (list of (14,3) mm) and 'joints_3d_vis' (list of (14,3) bool), frames in order
+    (evalmodel.py:291-320) -> (eval_list of dicts, total_gt)."""
+    eval_list, total_gt = [], 0
+    for t, gt in gts.items():
+        joints_3d, joints_3d_vis = gt["joints_3d"], gt["joints_3d_vis"]
+        if len(joints_3d) == 0:
+            continue
+        for pose in preds[t].copy():
+            pose = pose.T * 1000.
+            pelvis = (pose[11] + pose[12]) / 2
+            pose = pose[[0, 5, 7, 9, 11, 13, 15, 6, 8, 10, 12, 14, 16]]
+            pose = np.insert(pose, 1 * 3, pelvis).reshape(-1, 3)
+            mpjpes = []
+            for (g, gvis) in zip(joints_3d, joints_3d_vis):
+                vis = gvis[:, 0] > 0
+                mpjpes.append(np.mean(np.sqrt(np.sum((pose[vis, 0:3] - g[vis]) ** 2, axis=-1))))
+            eval_list.append({"mpjpe": float(np.min(mpjpes)), "gt_id": int(total_gt + np.argmin(mpjpes))})
+        total_gt += len(joints_3d)
+    return eval_list, total_gt
+
+
+def panoptic_metrics(eval_list, total_gt):
+    """AP@{25..150 mm}, recall, MPJPE, recall@500 (evalmodel.py:249-337)."""
+    def to_ap(threshold):
+        n = len(eval_list)
+        tp, fp, gt_det = np.zeros(n), np.zeros(n), []
+        for i, item in enumerate(eval_list):
+            if item["mpjpe"] < threshold and item["gt_id"] not in gt_det:
+                tp[i] = 1
+                gt_det.append(item["gt_id"])
+            else:
+                fp[i] = 1
+        tp, fp = np.cumsum(tp), np.cumsum(fp)
+        recall = tp / (total_gt + 1e-5)
+        precise = tp / (tp + fp + 1e-5)
+        for k in range(n - 2, -1, -1):
+            precise[k] = max(precise[k], precise[k + 1])
+        precise = np.concatenate(([0], precise, [0]))
+        recall = np.concatenate(([0], recall, [1]))
+        index = np.where(recall[1:] != recall[:-1])[0]
+        return np.sum((recall[index + 1] - recall[index]) * precise[index + 1]), recall[-2]
+    aps, recs = [], []
+    for t in np.arange(25, 155, 25):
+        a, r = to_ap(t)
+        aps.append(a)
+        recs.append(r)
+    gt_det, mp = [], []
+    for item in eval_list:
+        if item["mpjpe"] < 500 and item["gt_id"] not in gt_det:
+            mp.append(item["mpjpe"])
+            gt_det.append(item["gt_id"])
+    mpjpe = np.mean(mp) if len(mp) > 0 else np.inf
+    rec = len(np.unique([e["gt_id"] for e in eval_list if e["mpjpe"] < 500])) / total_gt
+    return aps, recs, mpjpe, rec

@@ -587,4 +587,54 @@ k_eval_pcp(const int* __restrict__ count, const float* __restrict__ joints, cons
     }
 }
 
+// ---- section 8f-1: EvaluatePanoptic.evaluate matching (evalmodel.py:291-320) -----------------------------
+// One thread per (sequence, frame, predicted pose): the prediction (tracker output, metres) is mapped
+// to the 14 evaluated Panoptic joints in millimetres -- COCO-17: nose, mid-hip = (l-hip + r-hip)/2, then
+// [5,7,9,11,13,15,6,8,10,12,14,16]; COCO-19: joints 1..14 -- and compared with every ground-truth body
+// of the frame: MPJPE over the visible joints, minimum and arg-minimum over the bodies.
+// gt [S][T][G][14][3] f64 (mm), vis [S][T][G][14] u8, n_gt [S][T];  out_mpjpe / out_gt [S][T][MT]
+// (out_gt = -1: frame without ground truth or slot beyond count).
+__global__ void k_eval_panoptic_match(const int* __restrict__ count, const float* __restrict__ joints,
+                                      const double* __restrict__ gt, const unsigned char* __restrict__ vis,
+                                      const int* __restrict__ n_gt, int S, int T, int G, int MT, int J,
+                                      double* __restrict__ out_mpjpe, int* __restrict__ out_gt) {
+    const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= (int64_t)S * T * MT) return;
+    const int q = (int)(it % MT);
+    const int64_t st = it / MT;
+    out_gt[it] = -1;
+    out_mpjpe[it] = 0.0;
+    const int ng = n_gt[st];
+    if (q >= count[st] || ng <= 0) return;
+    const float* p = joints + it * J * 3;
+    double m[14][3];
+    if (J == 17) {
+        const int map[12] = {5, 7, 9, 11, 13, 15, 6, 8, 10, 12, 14, 16};
+        for (int c = 0; c < 3; ++c) {
+            m[0][c] = (double)p[c] * 1000.0;
+            m[1][c] = ((double)p[11 * 3 + c] * 1000.0 + (double)p[12 * 3 + c] * 1000.0) / 2.0;
+        }
+        for (int j = 0; j < 12; ++j) for (int c = 0; c < 3; ++c) m[2 + j][c] = (double)p[map[j] * 3 + c] * 1000.0;
+    } else {
+        for (int j = 0; j < 14; ++j) for (int c = 0; c < 3; ++c) m[j][c] = (double)p[(j + 1) * 3 + c] * 1000.0;
+    }
+    double best = 0.0;
+    int arg = -1;
+    for (int g = 0; g < ng; ++g) {
+        const double* gg = gt + ((int64_t)st * G + g) * 14 * 3;
+        const unsigned char* vv = vis + ((int64_t)st * G + g) * 14;
+        double d[14];
+        int nvz = 0;
+        for (int j = 0; j < 14; ++j)
+            if (vv[j]) {
+                const double x = m[j][0] - gg[j * 3], y = m[j][1] - gg[j * 3 + 1], z = m[j][2] - gg[j * 3 + 2];
+                d[nvz++] = sqrt(x * x + y * y + z * z);
+            }
+        const double mp = np_sum(d, nvz) / (double)nvz;
+        if (arg < 0 || mp < best) { best = mp; arg = g; }      // np.argmin: first minimum; NaN never wins
+    }
+    out_mpjpe[it] = best;
+    out_gt[it] = arg;
+}
+
 }  // namespace pam
