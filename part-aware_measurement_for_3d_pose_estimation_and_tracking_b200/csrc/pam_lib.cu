@@ -126,8 +126,8 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
         if (t + 1 < T)
             stage_frame(dbuf + (cur ^ 1) * nfl_pad, cbuf + (cur ^ 1) * PAM_MAX_V, gd + (int64_t)(t + 1) * nfl,
                         gc + (t + 1) * c.V, nfl, c.V);
-        if (TEAM > 1) frame_step<WarpTeam<TEAM>>(ctx, c, sh, g, frame0 + t, dbuf + cur * nfl_pad, cbuf + cur * PAM_MAX_V, o);
-        else frame_step<SoloTeam>(ctx, c, sh, g, frame0 + t, dbuf + cur * nfl_pad, cbuf + cur * PAM_MAX_V, o);
+        if (TEAM > 1) frame_step<WarpTeam<TEAM>>(ctx, c, sh, g, frame0 + t, dbuf + cur * nfl_pad, cbuf + cur * PAM_MAX_V, o, gd, frame0);
+        else frame_step<SoloTeam>(ctx, c, sh, g, frame0 + t, dbuf + cur * nfl_pad, cbuf + cur * PAM_MAX_V, o, gd, frame0);
         if (o.count) o.count += 1;
         if (o.ids) o.ids += st_ids;
         if (o.joints) o.joints += st_joints;
@@ -137,6 +137,7 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
         __syncthreads();
         PAM_MARK(8);
     }
+    persist_views(ctx, c, sh, g, gd, frame0);
     store_state(ctx, c, sh, g);
     if (io.out_status && threadIdx.x == 0) io.out_status[s] = sh.hdr.status;
 #if defined(PAM_PHASE_TIMING)

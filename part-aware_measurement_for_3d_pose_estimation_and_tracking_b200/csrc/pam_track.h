@@ -56,6 +56,7 @@ struct TrkMeta {
     int view_time[PAM_MAX_V];
     int hist_time[PAM_HIST];
     signed char view_slot[PAM_MAX_V];   // camera -> position in the view list (dict key lookup), -1 = absent
+    signed char view_det[PAM_MAX_V];    // detection index of the view inside its own frame (lazy persistence)
 };
 
 inline void state_layout(DevCfg& c) {
@@ -130,7 +131,6 @@ struct SeqShared {
     int last[PAM_MAX_TRK];                   // ring index of the last pose
     signed char t2d[PAM_MAX_V][PAM_MAX_TRK];
     signed char d2t[PAM_MAX_V][PAM_MAX_D];
-    signed char vk[PAM_MAX_V][PAM_MAX_TRK];  // view slot written by add_pose
     ViewSrc* vsrc;    // [max_trk][V]         (arena) gathered views per track, dict order
     int gv_n[PAM_MAX_TRK];
     int do_update[PAM_MAX_TRK];
@@ -464,9 +464,14 @@ PAM_HD bool track_reported(const DevCfg& c, const SeqShared& sh, int i) {
 
 // `dets`/`counts` point at this frame's detections (staged in shared memory by the kernel).
 // The caller must synchronise the block after frame_step returns.
+// `dets`/`counts`: this frame's detections (staged in shared memory by the kernel).  `gin`: the launch's
+// detection tensor of this sequence in global memory, frame id `gin_frame0` at offset 0: a view that
+// was matched 1-3 frames ago is read from there instead of being copied into the track state every
+// frame; persist_views() writes the views of the launch into the state once, at the end.
 template <class Team, class Ctx>
 PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal& g, int frame,
-                       const float* dets /* [V][D][J][3] */, const int* counts /* [V] */, const FrameOut& out) {
+                       const float* dets /* [V][D][J][3] */, const int* counts /* [V] */, const FrameOut& out,
+                       const float* gin, int gin_frame0) {
     const int V = c.V, J = c.J, D = c.D, MT = c.max_trk;
     const int J3 = J * 3;
     if (sh.hdr.status != SEQ_OK) {   // uniform: status only changes between syncs
@@ -586,8 +591,8 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             int k = t.view_slot[cam];                 // view slot of this camera, -1 = not in the dict yet
             if (k < 0) { k = t.nviews++; t.view_cid[k] = cam; t.view_slot[cam] = (signed char)k; }
             t.view_time[k] = frame;
+            t.view_det[k] = sh.t2d[cam][i];
             t.already = 1;
-            sh.vk[cam][i] = (signed char)k;
         }
         int cnt = 0;
         if (t.already) {
@@ -600,7 +605,10 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
                 vs.cid = cam;
                 vs.T = age;
                 // a view matched this frame is read straight from the staged detections
-                vs.p = (age == 0) ? dets + (int64_t)(cam * D + sh.t2d[cam][i]) * J3 : g.view + (int64_t)(s * V + k) * J3;
+                const int tl = t.view_time[k] - gin_frame0;    // frame index inside this launch (< 0: earlier launch)
+                vs.p = (age == 0) ? dets + (int64_t)(cam * D + sh.t2d[cam][i]) * J3
+                     : (tl >= 0) ? gin + ((int64_t)tl * V * D + cam * D + t.view_det[k]) * J3
+                                 : g.view + (int64_t)(s * V + k) * J3;
             }
         }
         sh.gv_n[i] = cnt;
@@ -643,18 +651,6 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
                 double* r = sh.raw + (int64_t)(i * J + j) * 3;
                 r[0] = X[0]; r[1] = X[1]; r[2] = X[2];
             }
-        }
-    }
-    {   // J3 consecutive floats per matched (camera, track) pair; lanes stride over the elements
-        const int lanes = (ctx.nthreads() >= 32) ? 32 : ctx.nthreads();
-        const int grp = ctx.tid() / lanes, ngrp = ctx.nthreads() / lanes, lane = ctx.tid() - grp * lanes;
-        PAM_NOUNROLL for (int p = grp; p < V * n; p += ngrp) {
-            const int i = fast_div(p, c.inv_V), cam = p - i * V;
-            const int d = sh.t2d[cam][i];
-            if (d < 0) continue;
-            float* dst = g.view + ((int64_t)(sh.hdr.order[i] * V + sh.vk[cam][i])) * J3;
-            const float* src = dets + (int64_t)(cam * D + d) * J3;
-            PAM_NOUNROLL for (int e = lane; e < J3; e += lanes) dst[e] = src[e];
         }
     }
     PAM_FOR(cam, V) {
@@ -852,6 +848,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
                 PAM_NOUNROLL for (int cc2 = 0; cc2 < PAM_MAX_V; ++cc2) t.view_slot[cc2] = -1;
                 PAM_NOUNROLL for (int k = 0; k < t.nviews; ++k) {
                     t.view_cid[k] = sh.hyp_cam[h][k]; t.view_time[k] = frame; t.view_slot[sh.hyp_cam[h][k]] = (signed char)k;
+                    t.view_det[k] = sh.hyp_det[h][k];
                 }
                 t.hist_start = 0; t.hist_len = 1; t.hist_time[0] = frame;
                 sh.hyp_slot[h] = (signed char)s;
@@ -862,14 +859,34 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             const int h = it / J3, e = it % J3;
             const int s = sh.hyp_slot[h];
             if (s < 0) continue;
-            PAM_NOUNROLL for (int k = 0; k < sh.hyp_nviews[h]; ++k)
-                g.view[(int64_t)(s * V + k) * J3 + e] = dets[(int64_t)(sh.hyp_cam[h][k] * D + sh.hyp_det[h][k]) * J3 + e];
             g.hist[(int64_t)(s * PAM_HIST) * J3 + e] = sh.hyp_pose[(int64_t)h * J3 + e];
             g.vel[(int64_t)s * J3 + e] = 0.0f;
             if (e < J) g.nv[s * J + e] = sh.hyp_nvj[h * J + e];
         }
     }
     PAM_MARK(7);
+}
+
+// End of a launch: write the (v, u, conf) triples of every view that was matched during this launch
+// into the track state, so that later launches (and the host-side state read-back) find them there.
+template <class Ctx>
+PAM_HD void persist_views(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal& g, const float* gin,
+                          int gin_frame0) {
+    const int V = c.V, D = c.D, J3 = c.J * 3;
+    const int lanes = (ctx.nthreads() >= 32) ? 32 : ctx.nthreads();
+    const int grp = ctx.tid() / lanes, ngrp = ctx.nthreads() / lanes, lane = ctx.tid() - grp * lanes;
+    const int n = sh.hdr.ntracks;
+    PAM_NOUNROLL for (int p = grp; p < n * V; p += ngrp) {
+        const int i = fast_div(p, c.inv_V), k = p - i * V;
+        const int s = sh.hdr.order[i];
+        const TrkMeta& t = sh.trk[s];
+        if (k >= t.nviews) continue;
+        const int tl = t.view_time[k] - gin_frame0;
+        if (tl < 0) continue;                                   // matched in an earlier launch: already stored
+        const float* src = gin + ((int64_t)tl * V * D + t.view_cid[k] * D + t.view_det[k]) * J3;
+        float* dst = g.view + (int64_t)(s * V + k) * J3;
+        PAM_NOUNROLL for (int e = lane; e < J3; e += lanes) dst[e] = src[e];
+    }
 }
 
 }  // namespace pam

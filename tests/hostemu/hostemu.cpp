@@ -43,8 +43,10 @@ extern "C" int hostemu_track_sequences(const pam_config* cfg, const float* P, co
             o.joints = out_joints ? out_joints + ft * c.max_trk * c.J * 3 : nullptr;
             o.nviews = out_nviews ? out_nviews + ft * c.max_trk * c.J : nullptr;
             o.assoc = out_assoc ? out_assoc + ft * c.V * c.D : nullptr;
-            frame_step<SoloTeam>(ctx, c, *sh, g, frame0 + t, dets + ft * fstride, counts + ft * c.V, o);
+            frame_step<SoloTeam>(ctx, c, *sh, g, frame0 + t, dets + ft * fstride, counts + ft * c.V, o,
+                                 dets + (int64_t)s * T * fstride, frame0);
         }
+        persist_views(ctx, c, *sh, g, dets + (int64_t)s * T * fstride, frame0);
         store_state(ctx, c, *sh, g);
         if (status) status[s] = sh->hdr.status;
     }

@@ -25,3 +25,38 @@ def test_kernel_source_on_host_matches_oracle(shape, kw, T):
     oo, oa, _ = util.run_oracle(st)
     worst = util.compare_with_oracle(out, 0, st, oo, oa)
     assert out["count"].sum() > 0 and worst < 5e-4
+
+
+def test_kernel_source_chunked_launches_carry_state():
+    """Frames fed in several 'launches' (tracker state carried in the state buffer, stale views first read
+    from the launch's own input, then from the persisted copies) give the result of a single launch."""
+    import ctypes as C
+    import numpy as np
+    from tests.hostemu import build as hb
+    from pam_b200 import _capi, camera
+    st = synth.make_stream("shelf", 31, 90, miss_prob=0.25, outlier_prob=0.05)
+    cfg = util.stream_config(st, max_tracks=12)
+    one = util.run_hostemu([st], cfg)
+    lib = hb.load()
+    L = _capi.PamStateLayout()
+    assert lib.hostemu_state_layout(C.byref(cfg), C.byref(L)) == 0
+    state = np.zeros(L.seq_bytes, np.uint8)
+    P, RK, pos, F = camera.pack_cameras(camera.GetCameraParameters(st.rig))
+    parts = []
+    for a, b in ((0, 1), (1, 2), (2, 17), (17, 18), (18, 60), (60, 90)):
+        dets = np.ascontiguousarray(st.dets[None, a:b]); counts = np.ascontiguousarray(st.counts[None, a:b])
+        out = util.alloc_outputs(cfg, 1, b - a)
+        status = np.zeros(1, np.int32)
+        rc = lib.hostemu_track_sequences(C.byref(cfg), util.ptr(P), util.ptr(RK), util.ptr(pos), util.ptr(F), 1, b - a, a,
+                                         util.ptr(dets), util.ptr(counts), util.ptr(out["count"]), util.ptr(out["ids"]),
+                                         util.ptr(out["joints"]), util.ptr(out["nviews"]), util.ptr(out["assoc"]),
+                                         util.ptr(status), util.ptr(state))
+        assert rc == 0 and status[0] == 0
+        parts.append(out)
+    for k in ("count", "assoc"):
+        assert np.array_equal(np.concatenate([p[k] for p in parts], 1), one[k]), k
+    cnt = one["count"]
+    for k in ("ids", "joints", "nviews"):
+        cat = np.concatenate([p[k] for p in parts], 1)
+        for t in range(st.T):
+            assert np.array_equal(cat[0, t, :cnt[0, t]], one[k][0, t, :cnt[0, t]]), (k, t)
