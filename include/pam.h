@@ -77,12 +77,15 @@ typedef struct pam_state_layout {
     int64_t off_header;         /* int32: ntracks, next_id, status, frames_done, used_mask, order[16] */
     int64_t off_meta;           /* per slot, int32 x meta_ints                                      */
     int64_t off_hist;           /* double [slot][hist_len][J][3]  smoothed pose ring                */
-    int64_t off_view;           /* float  [slot][V][J][3]         last (v,u,conf) per view slot     */
+    int64_t off_view;           /* float  [slot][V][J][3]         last (v,u,conf) per view slot;
+                                   written at the END of every launch (inside a launch stale views
+                                   are read from the launch's own detection tensor)               */
     int64_t off_vel;            /* float  [slot][J][3]            velocity                          */
     int64_t off_nviews;         /* uint8  [slot][J]               views used for the last pose      */
     int32_t meta_ints;          /* ints per slot: id,hits,age,tsu,state,already,nviews,hist_start,
                                    hist_len, view_cid[8], view_time[8], hist_time[hist_ring],
-                                   then 8 bytes camera -> view-slot map                          */
+                                   then 8 bytes camera -> view-slot map and 8 bytes
+                                   detection index of each view inside its own frame             */
     int32_t hist_ring;          /* ring length                                                      */
     int32_t max_views;          /* 8                                                                */
     int32_t max_order;          /* 16                                                               */
