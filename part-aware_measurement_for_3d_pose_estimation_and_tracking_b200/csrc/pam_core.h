@@ -201,6 +201,16 @@ PAM_HD double epi_dist_f64(const double* F, double ua, double va, double ub, dou
     return fabs(ub * l0 + vb * l1 + l2) * inv;
 }
 
+// Raw form of the same: numerator t = l . x_b and squared norm n2 = l0^2 + l1^2 of the line F^T x_a, so
+// that "distance < thr" can be decided as t^2 < thr^2 n2 without a square root.
+PAM_HD void epi_raw_f64(const double* F, double ua, double va, double ub, double vb, double& t, double& n2) {
+    const double l0 = F[0] * ua + F[3] * va + F[6];
+    const double l1 = F[1] * ua + F[4] * va + F[7];
+    const double l2 = F[2] * ua + F[5] * va + F[8];
+    n2 = l0 * l0 + l1 * l1;
+    t = ub * l0 + vb * l1 + l2;
+}
+
 // cv::computeCorrespondEpilines arithmetic (double path): (a,b,c) = M x, nu = a^2+b^2,
 // nu = nu ? 1/sqrt(nu) : 1, scaled;  then utils/matching.py:82-83: |x . l| / sqrt(l0^2 + l1^2)
 // (= 1 after the scaling; for nu == 0 the reference divides by 0 and so does this).

@@ -30,6 +30,7 @@ inline int make_devcfg(const pam_config& p, DevCfg& c, std::string& err) {
     for (int T = 0; T < PAM_MAX_AGEW; ++T) c.w_age[T] = exp(-p.lambda_t * (double)T);
     c.inv_J = 1.0f / (float)c.J; c.inv_D = 1.0f / (float)c.D; c.inv_V = 1.0f / (float)c.V; c.inv_VD = 1.0f / (float)(c.V * c.D);
     c.inv_joint_thr = 1.0 / p.joint_threshold;
+    c.joint_thr2 = p.joint_threshold * p.joint_threshold;
     for (int dt = 0; dt < 16; ++dt) {
         c.inv_denom_tab[dt] = 1.0 / (p.alpha2d * (double)dt);
         c.inv_decay_tab[dt] = 1.0 / exp(p.lambda_a * (double)dt);

@@ -35,7 +35,7 @@ struct DevCfg {
     int rad[2];                              // [0] sigma, [1] arm_sigma
     double gw[2][PAM_MAX_RADIUS + 1];
     double w_age[PAM_MAX_AGEW];              // exp(-lambda_t * T), T = 0..stale_window
-    double inv_joint_thr;
+    double inv_joint_thr, joint_thr2;
     double inv_denom_tab[16];                // 1 / (alpha2d * dt), dt < 16
     double inv_decay_tab[16];                // 1 / exp(lambda_a * dt)
     double conf_thr, epi_thr, joint_thr, alpha2d, lambda_a, veto_believe, fail_limit;
@@ -359,8 +359,14 @@ PAM_HD int joint_update(const Team& tm, const DevCfg& c, const SeqShared& sh, in
             if (Team::size > 1 && (k & (Team::size - 1)) != tm.rank) continue;   // view pairs are dealt round-robin
             const double ub = vw.u(b), vb = vw.v(b);
             const int cb = vw.cid(b);
-            const double dab = epi_dist_f64(sh.Fc(ca, cb), ua, va, ub, vb);
-            const double dba = epi_dist_f64(sh.Fc(cb, ca), ub, vb, ua, va);
+            double tab, nab, tba, nba;
+            epi_raw_f64(sh.Fc(ca, cb), ua, va, ub, vb, tab, nab);
+            epi_raw_f64(sh.Fc(cb, ca), ub, vb, ua, va, tba, nba);
+            // both one-way distances below the threshold => their mean is too => no conflict; decided
+            // without a square root for the overwhelming majority of pairs
+            if (tab * tab < c.joint_thr2 * nab && tba * tba < c.joint_thr2 * nba) continue;
+            const double dab = fabs(tab) * ((nab == 0.0) ? 1.0 : rsqrt_f64(nab));
+            const double dba = fabs(tba) * ((nba == 0.0) ? 1.0 : rsqrt_f64(nba));
             const double A = 1.0 - (dab + dba) / 2.0 * c.inv_joint_thr;
             if (A < 0.0) conflict |= 1ull << (a * 8 + b);
         }
@@ -619,11 +625,11 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         sh.um_flag[cam][d] = 0;
         const int i = (d < sh.m[cam]) ? sh.d2t[cam][d] : -1;
         if (out.assoc) out.assoc[it] = (i >= 0) ? sh.trk[sh.hdr.order[i]].track_id : -1;
-        if (d >= sh.m[cam]) continue;
+        if (d >= sh.m[cam] || i >= 0) continue;   // the mean confidence only matters for unmatched detections
         const float* q = dets + (int64_t)(cam * D + d) * J3;
         const double b = mean_confidence(q, J);
         sh.believe[cam * D + d] = b;
-        sh.um_flag[cam][d] = (i < 0 && b > c.conf_thr) ? 1 : 0;
+        sh.um_flag[cam][d] = (b > c.conf_thr) ? 1 : 0;
     }
     ctx.sync();
     PAM_MARK(3);
