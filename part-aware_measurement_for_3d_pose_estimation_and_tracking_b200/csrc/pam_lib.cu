@@ -137,7 +137,7 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
         __syncthreads();
         PAM_MARK(8);
     }
-    persist_views(ctx, c, sh, g, gd, frame0);
+    persist_views(ctx, c, sh, g, gd, frame0, T > 0 ? dbuf + ((T - 1) & 1) * nfl_pad : nullptr, T - 1);
     store_state(ctx, c, sh, g);
     if (io.out_status && threadIdx.x == 0) io.out_status[s] = sh.hdr.status;
 #if defined(PAM_PHASE_TIMING)

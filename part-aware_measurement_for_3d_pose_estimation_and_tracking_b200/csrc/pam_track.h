@@ -877,7 +877,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
 // into the track state, so that later launches (and the host-side state read-back) find them there.
 template <class Ctx>
 PAM_HD void persist_views(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal& g, const float* gin,
-                          int gin_frame0) {
+                          int gin_frame0, const float* last_staged, int last_tl) {
     const int V = c.V, D = c.D, J3 = c.J * 3;
     const int lanes = (ctx.nthreads() >= 32) ? 32 : ctx.nthreads();
     const int grp = ctx.tid() / lanes, ngrp = ctx.nthreads() / lanes, lane = ctx.tid() - grp * lanes;
@@ -889,7 +889,10 @@ PAM_HD void persist_views(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlo
         if (k >= t.nviews) continue;
         const int tl = t.view_time[k] - gin_frame0;
         if (tl < 0) continue;                                   // matched in an earlier launch: already stored
-        const float* src = gin + ((int64_t)tl * V * D + t.view_cid[k] * D + t.view_det[k]) * J3;
+        // the launch's last frame is still staged on chip (for one-frame launches the input may even live in
+        // mapped host memory)
+        const float* src = (tl == last_tl && last_staged) ? last_staged + (int64_t)(t.view_cid[k] * D + t.view_det[k]) * J3
+                                                          : gin + ((int64_t)tl * V * D + t.view_cid[k] * D + t.view_det[k]) * J3;
         float* dst = g.view + (int64_t)(s * V + k) * J3;
         PAM_NOUNROLL for (int e = lane; e < J3; e += lanes) dst[e] = src[e];
     }

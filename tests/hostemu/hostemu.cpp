@@ -46,7 +46,7 @@ extern "C" int hostemu_track_sequences(const pam_config* cfg, const float* P, co
             frame_step<SoloTeam>(ctx, c, *sh, g, frame0 + t, dets + ft * fstride, counts + ft * c.V, o,
                                  dets + (int64_t)s * T * fstride, frame0);
         }
-        persist_views(ctx, c, *sh, g, dets + (int64_t)s * T * fstride, frame0);
+        persist_views(ctx, c, *sh, g, dets + (int64_t)s * T * fstride, frame0, (const float*)nullptr, -1);
         store_state(ctx, c, *sh, g);
         if (status) status[s] = sh->hdr.status;
     }
