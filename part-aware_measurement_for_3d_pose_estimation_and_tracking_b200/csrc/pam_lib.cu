@@ -47,15 +47,28 @@ struct DeviceCtx {
     }
 };
 
-// Asynchronous global -> shared staging of one frame's detections (LDGSTS / cp.async): issued for
-// frame t+1 while frame t is being processed, so the frame-serial chain never waits on HBM.
+// Asynchronous global -> shared staging of one frame's detections, issued for frame t+1 while frame t is
+// being processed, so the frame-serial chain never waits on HBM.  When the frame is a whole number of
+// 16-byte units (Shelf: 3360 B) ONE thread issues ONE bulk copy through the TMA engine
+// (cp.async.bulk, completion counted in bytes on an mbarrier -- UBLKCP in SASS); otherwise all threads
+// issue 4-byte LDGSTS copies.  The V per-camera counts always go through LDGSTS.
+__device__ __forceinline__ bool stage_is_bulk(const float* gsrc, int nfloats) {
+    return (nfloats & 3) == 0 && ((uintptr_t)gsrc & 15) == 0;
+}
 __device__ __forceinline__ void stage_frame(float* sdst, int* scnt, const float* gsrc, const int* gcnt, int nfloats,
-                                            int V) {
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(sdst);
-    if ((nfloats & 3) == 0 && ((uintptr_t)gsrc & 15) == 0) {
-        PAM_NOUNROLL for (int i = threadIdx.x; i < nfloats / 4; i += blockDim.x)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + i * 16), "l"(gsrc + i * 4) : "memory");
+                                            int V, unsigned long long* mbar, bool bulk) {
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(sdst), bar = (unsigned)__cvta_generic_to_shared(mbar);
+            const unsigned bytes = (unsigned)nfloats * 4u;
+            // order the generic-proxy reads of this buffer (two frames ago) before the async-proxy write
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+        }
     } else {
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(sdst);
         PAM_NOUNROLL for (int i = threadIdx.x; i < nfloats; i += blockDim.x)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbase + i * 4), "l"(gsrc + i) : "memory");
     }
@@ -64,7 +77,18 @@ __device__ __forceinline__ void stage_frame(float* sdst, int* scnt, const float*
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cbase + i * 4), "l"(gcnt + i) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// every thread: the LDGSTS copies of this thread are done; the bulk copy (if any) has delivered all bytes
+__device__ __forceinline__ void stage_wait(unsigned long long* mbar, unsigned parity, bool bulk) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (bulk) {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(mbar);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "PAM_WAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@!p bra PAM_WAIT_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+    }
+}
 
 // dynamic shared memory of k_track_sequences: [arena doubles][2 x frame floats][2 x V counts]
 static inline size_t frame_floats_padded(const DevCfg& c) { return ((size_t)c.V * c.D * c.J * 3 + 3) / 4 * 4; }
@@ -101,12 +125,20 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
     int* cbuf = (int*)(dbuf + 2 * nfl_pad);
     const float* gd = io.dets + (int64_t)s * io.seq_frames * nfl;
     const int* gc = io.counts + (int64_t)s * io.seq_frames * c.V;
-    if (T > 0) stage_frame(dbuf, cbuf, gd, gc, nfl, c.V);
-    if (threadIdx.x == 0) carve(c, sh, arena, g);
+    __shared__ __align__(8) unsigned long long mbar[2];       // one transaction barrier per detection buffer
+    const bool bulk = stage_is_bulk(gd, nfl);
+    if (threadIdx.x == 0) {
+        carve(c, sh, arena, g);
+        const unsigned b0 = (unsigned)__cvta_generic_to_shared(&mbar[0]), b1 = (unsigned)__cvta_generic_to_shared(&mbar[1]);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b0) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    if (T > 0) stage_frame(dbuf, cbuf, gd, gc, nfl, c.V, &mbar[0], bulk);
     load_cameras(ctx, c, sh, cc);
     load_state(ctx, c, sh, g);
-    stage_wait();
+    if (T > 0) stage_wait(&mbar[0], 0u, bulk);
     __syncthreads();
 #if defined(PAM_PHASE_TIMING)
     if (threadIdx.x == 0) { for (int k = 0; k < 24; ++k) sh.phase_cyc[k] = 0; sh.tlast = clock64(); }
@@ -125,7 +157,7 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
         const int cur = t & 1;
         if (t + 1 < T)
             stage_frame(dbuf + (cur ^ 1) * nfl_pad, cbuf + (cur ^ 1) * PAM_MAX_V, gd + (int64_t)(t + 1) * nfl,
-                        gc + (t + 1) * c.V, nfl, c.V);
+                        gc + (t + 1) * c.V, nfl, c.V, &mbar[cur ^ 1], bulk);
         if (TEAM > 1) frame_step<WarpTeam<TEAM>>(ctx, c, sh, g, frame0 + t, dbuf + cur * nfl_pad, cbuf + cur * PAM_MAX_V, o, gd, frame0);
         else frame_step<SoloTeam>(ctx, c, sh, g, frame0 + t, dbuf + cur * nfl_pad, cbuf + cur * PAM_MAX_V, o, gd, frame0);
         if (o.count) o.count += 1;
@@ -133,7 +165,8 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
         if (o.joints) o.joints += st_joints;
         if (o.nviews) o.nviews += st_nv;
         if (o.assoc) o.assoc += st_assoc;
-        stage_wait();
+        // buffer (t+1)&1 is used for the ((t+1)>>1)-th time: that is the parity of its barrier phase
+        if (t + 1 < T) stage_wait(&mbar[cur ^ 1], (unsigned)(((t + 1) >> 1) & 1), bulk);
         __syncthreads();
         PAM_MARK(8);
     }
