@@ -144,6 +144,14 @@ int pam_track_state_to_host(pam_handle* h, int32_t S, void* h_state);
 /* ---- stateless batched ops (device pointers, asynchronous on `stream`) ------------------------
  * Camera constants come from pam_set_cameras; J = cfg.num_joints; up to 32 cameras. */
 
+/* Camera ingest on the device (Camera.__init__ + GetCameraParameters, ivclabpose.py:35-46,162-181):
+ * d_K [V][3][3], d_RT [V][3][4] f32 -> d_RKinv [V][9] f32, d_pos [V][3] f64, d_F [V][V][9] f32, the arrays
+ * pam_set_cameras takes (P is an input of the reference, not derived).  No handle needed.  Float32
+ * arithmetic in the reference's association order; equal to the host ingest up to float32 rounding
+ * (torch/LAPACK round differently in the last bits), so parity runs use the host ingest. */
+int pam_camera_ingest(int32_t device, int32_t V, const float* d_K, const float* d_RT, float* d_RKinv, double* d_pos,
+                      float* d_F, void* stream);
+
 /* Camera.projectPoints_parallel (ivclabpose.py:91-98) for all cameras at once:
  * d_points3d [n_points][3] f64 -> d_out_vu [V][n_points][2] f64 as (v, u). */
 int pam_project_points(pam_handle* h, const double* d_points3d, int32_t n_points, double* d_out_vu, void* stream);

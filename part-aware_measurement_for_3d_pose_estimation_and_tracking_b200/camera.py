@@ -12,7 +12,7 @@ import numpy as np
 
 
 class Camera(object):
-    def __init__(self, cid, P, K, RT, F, w=640, h=480):
+    def __init__(self, cid, P, K, RT, F, w=640, h=480, RK_INV=None, position=None):
         self.cid = cid
         self.P = P
         self.K = K
@@ -20,9 +20,10 @@ class Camera(object):
         self.F = F
         self.w = w
         self.h = h
-        # R^-1 K^-1 in the dtype of the inputs (float32), centre from the 4x4 inverse (float64)
-        self.RK_INV = np.linalg.inv(RT[:, :3]) @ np.linalg.inv(K)
-        self.position = np.linalg.inv(np.vstack([RT, [0, 0, 0, 1]]))[:3, 3]
+        # R^-1 K^-1 in the dtype of the inputs (float32), centre from the 4x4 inverse (float64);
+        # the two keyword arguments carry the values of a device ingest (ingest_on_device)
+        self.RK_INV = np.linalg.inv(RT[:, :3]) @ np.linalg.inv(K) if RK_INV is None else RK_INV
+        self.position = np.linalg.inv(np.vstack([RT, [0, 0, 0, 1]]))[:3, 3] if position is None else position
 
     def undistort(self, im):
         return im
@@ -71,11 +72,39 @@ def fundamental_tensor(K: np.ndarray, RT: np.ndarray) -> np.ndarray:
     return F.numpy()
 
 
-def GetCameraParameters(camera_parameter, im_width=640, im_height=480) -> List[Camera]:
-    """``{'P': (V,3,4), 'K': (V,3,3), 'RT': (V,3,4)}`` (a ``camera_parameter.pickle``) -> cameras."""
+def ingest_on_device(K: np.ndarray, RT: np.ndarray, device: int = 0):
+    """``pam_camera_ingest``: (V,3,3), (V,3,4) float32 -> ``RK_INV (V,3,3) f32, position (V,3) f64,
+    F (V,V,3,3) f32`` computed by one kernel launch (961 matrices at V=31).
+    Equal to the host ingest up to float32 rounding, see include/pam.h."""
+    import torch
+    from . import _capi
+
+    lib = _capi.load_library()
+    V = len(K)
+    dev = torch.device("cuda", device)
+    dK = torch.from_numpy(np.ascontiguousarray(K, np.float32)).to(dev)
+    dRT = torch.from_numpy(np.ascontiguousarray(RT, np.float32)).to(dev)
+    dRK = torch.empty((V, 3, 3), dtype=torch.float32, device=dev)
+    dpos = torch.empty((V, 3), dtype=torch.float64, device=dev)
+    dF = torch.empty((V, V, 3, 3), dtype=torch.float32, device=dev)
+    rc = lib.pam_camera_ingest(device, V, dK.data_ptr(), dRT.data_ptr(), dRK.data_ptr(), dpos.data_ptr(), dF.data_ptr(),
+                               torch.cuda.current_stream(dev).cuda_stream)
+    if rc != 0:
+        raise RuntimeError("pam_camera_ingest: " + lib.pam_last_error(None).decode())
+    return dRK.cpu().numpy(), dpos.cpu().numpy(), dF.cpu().numpy()
+
+
+def GetCameraParameters(camera_parameter, im_width=640, im_height=480, device=None) -> List[Camera]:
+    """``{'P': (V,3,4), 'K': (V,3,3), 'RT': (V,3,4)}`` (a ``camera_parameter.pickle``) -> cameras.
+    ``device=None`` (default) evaluates the reference's float32 host expression, bit-identical constants;
+    ``device=<cuda index>`` derives them with ``pam_camera_ingest`` (float32-rounding level differences)."""
     P = np.asarray(camera_parameter["P"]).astype(np.float32)
     K = np.asarray(camera_parameter["K"]).astype(np.float32)
     RT = np.asarray(camera_parameter["RT"]).astype(np.float32)
+    if device is not None:
+        RK, pos, F = ingest_on_device(K, RT, device)
+        return [Camera(j, P[j], K[j], RT[j], F[j], w=im_width, h=im_height, RK_INV=RK[j], position=pos[j])
+                for j in range(len(P))]
     F = fundamental_tensor(K, RT)
     return [Camera(j, P[j], K[j], RT[j], F[j], w=im_width, h=im_height) for j in range(len(P))]
 

@@ -45,6 +45,94 @@ __global__ void k_project_points(const float* __restrict__ P, int V, const doubl
     out[(int64_t)it * 2 + 1] = a / w;
 }
 
+// ---- a1: camera ingest (ivclabpose.py:35-46,162-181): K, RT -> RK_INV, centre, V x V fundamental tensor ----
+// One thread per ordered camera pair.  Float32 with fused multiply-adds in the association order of
+// the reference's torch expression  K_a^-T (R_a R_b^T) K_b^T [K_b R_b R_a^T (t_a - R_a R_b^T t_b)]_x ;
+// the inverse is the adjugate form.  The reference's LAPACK/MKL kernels round differently in the
+// last bits, so this op matches the host ingest (camera.fundamental_tensor) to float32 rounding, not
+// bit for bit; the tracker's default ingest stays on the host for that reason.
+__device__ __forceinline__ void mm33f(const float* A, const float* B, float* C) {      // C = A B
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C[i * 3 + j] = fmaf(A[i * 3 + 2], B[6 + j], fmaf(A[i * 3 + 1], B[3 + j], A[i * 3] * B[j]));
+}
+__device__ __forceinline__ void mm33f_bt(const float* A, const float* B, float* C) {   // C = A B^T
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C[i * 3 + j] = fmaf(A[i * 3 + 2], B[j * 3 + 2], fmaf(A[i * 3 + 1], B[j * 3 + 1], A[i * 3] * B[j * 3]));
+}
+__device__ __forceinline__ void mv33f(const float* A, const float* x, float* y) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) y[i] = fmaf(A[i * 3 + 2], x[2], fmaf(A[i * 3 + 1], x[1], A[i * 3] * x[0]));
+}
+template <typename T>
+__device__ __forceinline__ void inv33(const T* A, T* I) {
+    const T c0 = A[4] * A[8] - A[5] * A[7], c1 = A[5] * A[6] - A[3] * A[8], c2 = A[3] * A[7] - A[4] * A[6];
+    const T r = (T)1 / (A[0] * c0 + A[1] * c1 + A[2] * c2);
+    I[0] = c0 * r; I[1] = (A[2] * A[7] - A[1] * A[8]) * r; I[2] = (A[1] * A[5] - A[2] * A[4]) * r;
+    I[3] = c1 * r; I[4] = (A[0] * A[8] - A[2] * A[6]) * r; I[5] = (A[2] * A[3] - A[0] * A[5]) * r;
+    I[6] = c2 * r; I[7] = (A[1] * A[6] - A[0] * A[7]) * r; I[8] = (A[0] * A[4] - A[1] * A[3]) * r;
+}
+__global__ void k_camera_ingest(int V, const float* __restrict__ K, const float* __restrict__ RT,
+                                float* __restrict__ RKinv, double* __restrict__ pos, float* __restrict__ F) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= V * V) return;
+    const int a = it / V, b = it - a * V;
+    float Ka[9], Kb[9], Ra[9], Rb[9], ta[3], tb[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { Ka[k] = K[a * 9 + k]; Kb[k] = K[b * 9 + k]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { Ra[i * 3 + j] = RT[a * 12 + i * 4 + j]; Rb[i * 3 + j] = RT[b * 12 + i * 4 + j]; }
+        ta[i] = RT[a * 12 + i * 4 + 3]; tb[i] = RT[b * 12 + i * 4 + 3];
+    }
+    float Kai[9], KaiT[9], Rab[9], M1[9], M2[9], KR[9], KRR[9], v[3], e[3];
+    inv33<float>(Ka, Kai);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) KaiT[i * 3 + j] = Kai[j * 3 + i];
+    mm33f_bt(Ra, Rb, Rab);                 // R_a R_b^T
+    mm33f(KaiT, Rab, M1);
+    mm33f_bt(M1, Kb, M2);                  // ... K_b^T
+    mm33f(Kb, Rb, KR);
+    mm33f_bt(KR, Ra, KRR);                 // K_b R_b R_a^T
+    mv33f(Rab, tb, v);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = ta[i] - v[i];
+    mv33f(KRR, v, e);
+    const float ex[9] = {0.f, -e[2], e[1], e[2], 0.f, -e[0], -e[1], e[0], 0.f};
+    float Fm[9];
+    mm33f(M2, ex, Fm);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sum += Fm[k];
+    if (sum == 0.f)                        // "to avoid nan", ivclabpose.py:176-177
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Fm[k] += 1e-12f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) F[(int64_t)it * 9 + k] = Fm[k];
+    if (a != b) return;
+    // Camera.__init__: RK_INV = R^-1 K^-1 (float32); centre = -R^-1 t from the float64 4 x 4 inverse
+    float Rai[9], RK[9];
+    inv33<float>(Ra, Rai);
+    mm33f(Rai, Kai, RK);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) RKinv[a * 9 + k] = RK[k];
+    double Rd[9], Rdi[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Rd[k] = (double)Ra[k];
+    inv33<double>(Rd, Rdi);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        pos[a * 3 + i] = -(Rdi[i * 3] * (double)ta[0] + Rdi[i * 3 + 1] * (double)ta[1] + Rdi[i * 3 + 2] * (double)ta[2]);
+}
+
 // ---- a3: affinity of every (camera, track, detection) ---------------------------------------------
 // tracks X [n][J][3], dt [n]; dets [V][mmax][J][3] f64 (v,u,conf), counts [V]; aff [V][n][mmax]
 __global__ void k_assoc_affinity(const float* __restrict__ P, int V, const double* __restrict__ X,

@@ -76,3 +76,13 @@ print(f"dense frame: V={V} P={P} J={J} M={M}")
 for name, ms, b, fl in rows:
     print(f"{name:55s} {ms:8.3f} ms  {b/1e6:9.2f} MB  {b/ms/1e6:8.1f} GB/s ({100*b/ms/1e6/PEAK:5.1f}% of measured HBM peak)"
           + (f"  ~{fl/ms/1e9:6.2f} TFLOP/s fp64" if fl else ""))
+# camera ingest, 31 cameras -> 961 fundamental matrices: device kernel vs the host's float32 torch loop
+Kd = torch.from_numpy(np.stack([c.K for c in cams])).cuda(); RTd = torch.from_numpy(np.stack([c.RT for c in cams])).cuda()
+RKd = torch.empty((V, 9), dtype=torch.float32, device="cuda"); posd = torch.empty((V, 3), dtype=torch.float64, device="cuda")
+Fd = torch.empty((V, V, 9), dtype=torch.float32, device="cuda")
+def ingest():
+    rc = o.lib.pam_camera_ingest(0, V, Kd.data_ptr(), RTd.data_ptr(), RKd.data_ptr(), posd.data_ptr(), Fd.data_ptr(), o._stream())
+    assert rc == 0
+ms = timeit(ingest)
+t0 = time.perf_counter(); camera.fundamental_tensor(np.stack([c.K for c in cams]), np.stack([c.RT for c in cams])); host_ms = (time.perf_counter() - t0) * 1e3
+print(f"pam_camera_ingest (31 cameras, 961 matrices)            {ms:8.3f} ms on the device; host float32 torch loop {host_ms:.1f} ms")
