@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--sequences", type=int, default=1184, help="independent sequences per GPU (148 SMs x 8 CTAs; 1776 = 12 per SM is ~4% faster but needs 35 GB of host memory per rank)")
     ap.add_argument("--frames", type=int, default=None, help="frames per sequence (default: the shape's 3200)")
     ap.add_argument("--shape", default=SHAPE)
-    ap.add_argument("--cpu-frames", type=int, default=2000, help="frames of the cpu_baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=4500, help="frames of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -95,7 +95,9 @@ def bind_to_gpu_numa_node(device_index):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled during the timed region (B200_PROFILING.md recipe: the
+    nvidia-smi query below; read through NVML directly when pynvml is importable, so that a sub-second
+    timed region still gets tens of samples)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -104,8 +106,30 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_evt = index, [], threading.Event()
 
+    def _nvml_row(self):
+        """Same fields through NVML (what nvidia-smi reads), cheap enough to sample every 20 ms."""
+        import pynvml as nv
+        if not hasattr(self, "_h"):
+            nv.nvmlInit()
+            self._h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self._max = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+        sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = int(get(self._h))
+        act = lambda bit: "Active" if r & bit else "Not Active"
+        # bits: sw_power_cap 0x4, hw_slowdown 0x8, sw_thermal 0x20, hw_thermal 0x40 (nvml.h)
+        return [str(sm), str(self._max), "", act(0x8), act(0x40), act(0x20), act(0x4)]
+
     def run(self):
+        use_nvml = True
         while not self.stop_evt.is_set():
+            if use_nvml:
+                try:
+                    self.rows.append(self._nvml_row())
+                    self.stop_evt.wait(0.02)
+                    continue
+                except Exception:
+                    use_nvml = False
             try:
                 o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout

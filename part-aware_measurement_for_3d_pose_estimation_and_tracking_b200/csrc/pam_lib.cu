@@ -490,6 +490,15 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
     // the kernel of chunk k (three streams; tracker state stays in HBM between the chunk launches).
     if (!h->ws_in) CK(cudaStreamCreateWithFlags(&h->ws_in, cudaStreamNonBlocking));
     if (!h->ws_out) CK(cudaStreamCreateWithFlags(&h->ws_out, cudaStreamNonBlocking));
+    // an error return below must not leave copies into / out of the caller's buffers in flight
+    struct DrainOnError {
+        pam_handle* h;
+        bool armed;
+        ~DrainOnError() {
+            if (!armed) return;
+            cudaStreamSynchronize(h->ws_in); cudaStreamSynchronize(h->ws_stream); cudaStreamSynchronize(h->ws_out);
+        }
+    } drain{h, true};
     int nchunks = T / 50;   // PCIe-bound: more, smaller chunks shorten the pipeline fill and drain
     const char* nce = getenv("PAM_HOST_CHUNKS");
     if (nce) nchunks = atoi(nce);
@@ -535,6 +544,7 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
         if (h_out_assoc) CK(chunk2d(h_out_assoc, h->ws_assoc.p, f_assoc, t0, n, cudaMemcpyDeviceToHost, h->ws_out));
     }
     CK(cudaStreamSynchronize(h->ws_out));
+    drain.armed = false;
     return pam_track_status(h, h->ws_state.p, S, nullptr, st);
 }
 
