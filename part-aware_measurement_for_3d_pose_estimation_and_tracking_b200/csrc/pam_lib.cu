@@ -4,6 +4,8 @@
 //        (see __graft_entry__.build()).  No CPU fallback: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -172,7 +174,13 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
     }
     persist_views(ctx, c, sh, g, gd, frame0, T > 0 ? dbuf + ((T - 1) & 1) * nfl_pad : nullptr, T - 1);
     store_state(ctx, c, sh, g);
-    if (io.out_status && threadIdx.x == 0) io.out_status[s] = sh.hdr.status;
+    if (io.out_status && threadIdx.x == 0) {
+        // the status word may live in mapped host memory and be polled by the caller (small-job path):
+        // everything this CTA wrote for the host (ordered before this point by the frame barriers) must be
+        // visible system-wide first
+        __threadfence_system();
+        *(volatile int*)(io.out_status + s) = sh.hdr.status;
+    }
 #if defined(PAM_PHASE_TIMING)
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         static const char* nm[9] = {"1 age+reproj", "2 affinity", "3 assign", "4 add_pose+believe", "5 filter+dlt",
@@ -465,9 +473,25 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
                        h_out_ids ? (int32_t*)(dz + o_ids) : nullptr, h_out_joints ? (float*)(dz + o_joints) : nullptr,
                        h_out_nviews ? (uint8_t*)(dz + o_nv) : nullptr, h_out_assoc ? (int32_t*)(dz + o_assoc) : nullptr, T,
                        (int*)(dz + o_status)};
+            // completion is detected by polling the status words the CTAs write last (a few us sooner
+            // than a stream synchronisation wakes up); bounded, then the stream is synchronised anyway
+            volatile int32_t* stv = (volatile int32_t*)(z + o_status);
+            const int32_t pending = 0x7fffffff;
+            for (int s = 0; s < S; ++s) stv[s] = pending;
             int rc = launch_track(h, h->ws_state.p, S, T, frame0, io, st);
             if (rc != PAM_OK) return rc;
-            CK(cudaStreamSynchronize(st));
+            {
+                const auto t0 = std::chrono::steady_clock::now();
+                const auto budget = std::chrono::microseconds(200 + 40 * (int64_t)T);
+                bool done = false;
+                for (int spin = 0; !done; ++spin) {
+                    done = true;
+                    for (int s = 0; s < S && done; ++s) done = stv[s] != pending;
+                    if (!done && (spin & 63) == 63 && std::chrono::steady_clock::now() - t0 > budget) break;
+                }
+                std::atomic_thread_fence(std::memory_order_acquire);
+                if (!done) CK(cudaStreamSynchronize(st));
+            }
             memcpy(h_out_count, z + o_count, b_count);
             if (h_out_ids) memcpy(h_out_ids, z + o_ids, b_ids);
             if (h_out_joints) memcpy(h_out_joints, z + o_joints, b_joints);
