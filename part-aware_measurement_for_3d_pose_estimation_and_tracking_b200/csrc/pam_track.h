@@ -153,8 +153,7 @@ struct SeqShared {
     unsigned char* hyp_nvj;    // [max_hyp][J]   (global scratch)
     double* hyp_cost;          // [max_hyp][D]   (global scratch)
     // output
-    int out_n;
-    signed char out_slot[PAM_MAX_TRK];
+    signed char life_flag[PAM_MAX_TRK];      // phase 7: bit 0 = track kept, bit 1 = reported this frame
 #if defined(PAM_PHASE_TIMING)
     long long phase_cyc[24];
     long long tlast;
@@ -246,6 +245,10 @@ struct WarpTeam {
 #endif
 
 #define PAM_FOR(i, N) PAM_NOUNROLL for (int i = ctx.tid(), _n_##i = (N), _s_##i = ctx.nthreads(); i < _n_##i; i += _s_##i)
+// Same, dealt from the highest thread downwards: small independent loops of a phase go to the threads
+// (warps) that the phase's main loop leaves idle, so they run beside it instead of after it.
+#define PAM_FOR_REV(i, N) \
+    PAM_NOUNROLL for (int i = ctx.nthreads() - 1 - ctx.tid(), _n_##i = (N), _s_##i = ctx.nthreads(); i < _n_##i; i += _s_##i)
 
 // camera constants: f32 in global memory (the reference's dtypes), widened once into shared.
 struct CamConst {
@@ -503,14 +506,16 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         }
         sh.fail[i] = 0;
     }
-    PAM_FOR(cc, V) {
+    PAM_FOR_REV(cc, V) {
         int mm = counts[cc];
         if (mm > D || mm < 0) { sh.hdr.status = SEQ_ERR_DET_OVERFLOW; mm = 0; }
         sh.m[cc] = mm;
         sh.conflict[cc] = 0;
     }
-    PAM_FOR(i, PAM_MAX_V * PAM_MAX_TRK / 4) ((int*)sh.t2d)[i] = -1;
-    PAM_FOR(i, PAM_MAX_V * PAM_MAX_D / 4) ((int*)sh.d2t)[i] = -1;
+    PAM_FOR_REV(i, PAM_MAX_V * PAM_MAX_TRK / 4 + PAM_MAX_V * PAM_MAX_D / 4) {
+        if (i < PAM_MAX_V * PAM_MAX_TRK / 4) ((int*)sh.t2d)[i] = -1;
+        else ((int*)sh.d2t)[i - PAM_MAX_V * PAM_MAX_TRK / 4] = -1;
+    }
     ctx.sync();
     PAM_MARK(0);
 
@@ -620,7 +625,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         sh.gv_n[i] = cnt;
         sh.do_update[i] = (t.already && cnt >= 2) ? 1 : 0;
     }
-    PAM_FOR(it, V * D) {
+    PAM_FOR_REV(it, V * D) {
         const int cam = fast_div(it, c.inv_D), d = it - cam * D;
         sh.um_flag[cam][d] = 0;
         const int i = (d < sh.m[cam]) ? sh.d2t[cam][d] : -1;
@@ -659,7 +664,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             }
         }
     }
-    PAM_FOR(cam, V) {
+    PAM_FOR_REV(cam, V) {
         int k = 0;
         PAM_NOUNROLL for (int d = 0; d < sh.m[cam]; ++d)
             if (sh.um_flag[cam][d]) sh.um[cam][k++] = (signed char)d;
@@ -729,36 +734,32 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
 
     // ---- phase 7: life-cycle (IterativeTracker.py:253-274), reported ids, reap (:178), and the
     //      decision whether new-track initialisation has anything to do ---------------------------
-    if (ctx.tid() == 0) {
-        int k = 0, wr = 0;
-        PAM_NOUNROLL for (int i = 0; i < n; ++i) {
-            const int s = sh.hdr.order[i];
-            TrkMeta& t = sh.trk[s];
-            if (sh.do_update[i] && !((double)sh.fail[i] > c.fail_limit) && t.hist_len >= PAM_HIST)
-                sh.hdr.status = SEQ_ERR_HIST_OVERFLOW;
-            if (track_ok(c, sh, i)) {
-                t.hist_len += 1;
-                if (frame - t.hist_time[t.hist_start] > c.max_age) {
-                    t.hist_start = (t.hist_start + 1) % PAM_HIST;
-                    t.hist_len -= 1;
-                }
-                t.hits += 1;
-                t.tsu = 0;
-                if (t.state == ST_TENTATIVE && t.hits >= c.n_init) t.state = ST_CONFIRMED;
-                if (t.state == ST_CONFIRMED) {
-                    if (out.ids) out.ids[k] = t.track_id;
-                    ++k;
-                }
-            } else {
-                if (t.state == ST_TENTATIVE && !t.already) t.state = ST_DELETED;
-                else if (t.tsu >= c.max_age) t.state = ST_DELETED;
+    // 7a, one thread per track: counters and state transitions; bit 0 of life_flag = keep, bit 1 = reported
+    PAM_FOR(i, n) {
+        const int s = sh.hdr.order[i];
+        TrkMeta& t = sh.trk[s];
+        if (sh.do_update[i] && !((double)sh.fail[i] > c.fail_limit) && t.hist_len >= PAM_HIST)
+            sh.hdr.status = SEQ_ERR_HIST_OVERFLOW;
+        int flag = 0;
+        if (track_ok(c, sh, i)) {
+            t.hist_len += 1;
+            if (frame - t.hist_time[t.hist_start] > c.max_age) {
+                t.hist_start = (t.hist_start + 1) % PAM_HIST;
+                t.hist_len -= 1;
             }
-            if (t.state == ST_DELETED) sh.hdr.used_mask &= ~(1u << s);
-            else sh.hdr.order[wr++] = s;
+            t.hits += 1;
+            t.tsu = 0;
+            if (t.state == ST_TENTATIVE && t.hits >= c.n_init) t.state = ST_CONFIRMED;
+            if (t.state == ST_CONFIRMED) flag |= 2;
+        } else {
+            if (t.state == ST_TENTATIVE && !t.already) t.state = ST_DELETED;
+            else if (t.tsu >= c.max_age) t.state = ST_DELETED;
         }
-        sh.hdr.ntracks = wr;
-        sh.hdr.frames_done += 1;
-        if (out.count) *out.count = k;
+        if (t.state != ST_DELETED) flag |= 1;
+        sh.life_flag[i] = (signed char)flag;
+    }
+    // ... while the last thread decides whether new-track initialisation has anything to do
+    if (ctx.tid() == ctx.nthreads() - 1) {
         int cams_with = 0;
         PAM_NOUNROLL for (int cam = 0; cam < V; ++cam) cams_with += (sh.um_n[cam] > 0);
         // a hypothesis needs views from two cameras to become a track (hypothesis.size() > 1)
@@ -770,6 +771,24 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             }
             sh.hyp_n = sh.um_n[0];
         }
+    }
+    ctx.sync();
+    // 7b, one thread: reported ids in track order, compaction of the track list
+    if (ctx.tid() == 0) {
+        int k = 0, wr = 0;
+        PAM_NOUNROLL for (int i = 0; i < n; ++i) {
+            const int s = sh.hdr.order[i];
+            const int flag = sh.life_flag[i];
+            if (flag & 2) {
+                if (out.ids) out.ids[k] = sh.trk[s].track_id;
+                ++k;
+            }
+            if (flag & 1) sh.hdr.order[wr++] = s;
+            else sh.hdr.used_mask &= ~(1u << s);
+        }
+        sh.hdr.ntracks = wr;
+        sh.hdr.frames_done += 1;
+        if (out.count) *out.count = k;
     }
     ctx.sync();
     PAM_MARK(6);
