@@ -133,6 +133,8 @@ struct SeqShared {
     signed char d2t[PAM_MAX_V][PAM_MAX_D];
     ViewSrc* vsrc;    // [max_trk][V]         (arena) gathered views per track, dict order
     int gv_n[PAM_MAX_TRK];
+    int new_view[PAM_MAX_TRK];               // a matched camera is not in the track's view list yet
+    int any_conflict;                        // some camera needs the full assignment solver
     int do_update[PAM_MAX_TRK];
     int fail[PAM_MAX_TRK];                   // joints left with < 2 views
     int conflict[PAM_MAX_V];                 // camera needs the full assignment solver
@@ -153,6 +155,7 @@ struct SeqShared {
     unsigned char* hyp_nvj;    // [max_hyp][J]   (global scratch)
     double* hyp_cost;          // [max_hyp][D]   (global scratch)
     // output
+    signed char out_row[PAM_MAX_TRK];        // phase 6: output row of a reported track, -1 = not reported
     signed char life_flag[PAM_MAX_TRK];      // phase 7: bit 0 = track kept, bit 1 = reported this frame
 #if defined(PAM_PHASE_TIMING)
     long long phase_cyc[24];
@@ -505,7 +508,9 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             sh.inv_decay[i] = 1.0 / exp(c.lambda_a * (double)dt);
         }
         sh.fail[i] = 0;
+        sh.new_view[i] = 0;
     }
+    if (ctx.tid() == ctx.nthreads() - 1) sh.any_conflict = 0;
     PAM_FOR_REV(cc, V) {
         int mm = counts[cc];
         if (mm > D || mm < 0) { sh.hdr.status = SEQ_ERR_DET_OVERFLOW; mm = 0; }
@@ -554,6 +559,17 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
     // matrix already form a matching (at most one per row and per column) every optimal assignment
     // contains exactly those pairs, so they are taken directly; otherwise the camera is flagged
     // and solved with the full shortest-augmenting-path algorithm below.
+    // The thread that finds the match of (track, camera) applies it to the track's view list at once
+    // (add_pose, IterativeTracker.py:289-298): a pair that is the only positive entry of its row and of
+    // its column belongs to every optimal assignment, so this stays valid if the camera is re-solved below.
+    // A camera that is not in the list yet is appended by the per-track pass (insertion order = camera order).
+    auto apply_match = [&](int i, int cam, int d) {
+        TrkMeta& t = sh.trk[sh.hdr.order[i]];
+        const int k = t.view_slot[cam];               // view slot of this camera, -1 = not in the dict yet
+        if (k >= 0) { t.view_time[k] = frame; t.view_det[k] = (signed char)d; }
+        else sh.new_view[i] = 1;
+        t.already = 1;
+    };
     PAM_FOR(it, V * n) {
         const int i = fast_div(it, c.inv_V), cam = it - i * V;
         const int mm = sh.m[cam];
@@ -564,66 +580,80 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         if (cnt == 1) {
             int col = 0;
             PAM_NOUNROLL for (int k = 0; k < n; ++k) col += (A[k * D + arg] > 0.0) ? 1 : 0;
-            if (col == 1) { sh.t2d[cam][i] = (signed char)arg; sh.d2t[cam][arg] = (signed char)i; }
-            else sh.conflict[cam] = 1;
+            if (col == 1) {
+                sh.t2d[cam][i] = (signed char)arg; sh.d2t[cam][arg] = (signed char)i;
+                apply_match(i, cam, arg);
+            } else { sh.conflict[cam] = 1; sh.any_conflict = 1; }
         } else if (cnt > 1) {
-            sh.conflict[cam] = 1;
+            sh.conflict[cam] = 1; sh.any_conflict = 1;
         }
     }
     ctx.sync();
-    {
-        int any = 0;
-        PAM_NOUNROLL for (int cam = 0; cam < V; ++cam) any |= sh.conflict[cam];
-        if (any) {   // uniform
-            PAM_FOR(cam, V) {
-                if (!sh.conflict[cam]) continue;
-                const int mm = sh.m[cam];
-                const double* A = sh.aff + (int64_t)cam * MT * D;
-                PAM_NOUNROLL for (int i = 0; i < n; ++i) sh.t2d[cam][i] = -1;
-                PAM_NOUNROLL for (int d = 0; d < D; ++d) sh.d2t[cam][d] = -1;
-                int col4row[PAM_MAX_TRK];
-                lsap_solve<PAM_MAX_TRK>(n, mm, [&](int i, int d) { return -A[i * D + d]; }, col4row);
-                PAM_NOUNROLL for (int i = 0; i < n; ++i) {
-                    int d = col4row[i];
-                    if (d >= 0 && A[i * D + d] > 0.0) { sh.t2d[cam][i] = (signed char)d; sh.d2t[cam][d] = (signed char)i; }
-                }
+    if (sh.any_conflict) {   // uniform
+        PAM_FOR(cam, V) {
+            if (!sh.conflict[cam]) continue;
+            const int mm = sh.m[cam];
+            const double* A = sh.aff + (int64_t)cam * MT * D;
+            PAM_NOUNROLL for (int i = 0; i < n; ++i) sh.t2d[cam][i] = -1;
+            PAM_NOUNROLL for (int d = 0; d < D; ++d) sh.d2t[cam][d] = -1;
+            int col4row[PAM_MAX_TRK];
+            lsap_solve<PAM_MAX_TRK>(n, mm, [&](int i, int d) { return -A[i * D + d]; }, col4row);
+            PAM_NOUNROLL for (int i = 0; i < n; ++i) {
+                int d = col4row[i];
+                if (d >= 0 && A[i * D + d] > 0.0) { sh.t2d[cam][i] = (signed char)d; sh.d2t[cam][d] = (signed char)i; }
             }
-            ctx.sync();
         }
+        ctx.sync();
+        PAM_FOR(it, V * n) {
+            const int i = fast_div(it, c.inv_V), cam = it - i * V;
+            if (sh.conflict[cam] && sh.t2d[cam][i] >= 0) apply_match(i, cam, sh.t2d[cam][i]);
+        }
+        ctx.sync();
     }
     PAM_MARK(2);
 
-    // ---- phase 4: add_pose in camera order (IterativeTracker.py:289-298), gather the usable views
-    //      of every track (:310-325); mean confidence of every detection (calculate.py:8-14) ------
-    PAM_FOR(i, n) {
-        TrkMeta& t = sh.trk[sh.hdr.order[i]];
-        PAM_NOUNROLL for (int cam = 0; cam < V; ++cam) {
-            if (sh.t2d[cam][i] < 0) continue;
-            int k = t.view_slot[cam];                 // view slot of this camera, -1 = not in the dict yet
-            if (k < 0) { k = t.nviews++; t.view_cid[k] = cam; t.view_slot[cam] = (signed char)k; }
-            t.view_time[k] = frame;
-            t.view_det[k] = sh.t2d[cam][i];
-            t.already = 1;
+    // ---- phase 4: gather the usable views of every track in dict-insertion order
+    //      (IterativeTracker.py:310-325); mean confidence of every unmatched detection (calculate.py:8-14)
+    PAM_FOR(it, n * V) {
+        const int i = fast_div(it, c.inv_V), k = it - i * V;
+        const int s = sh.hdr.order[i];
+        TrkMeta& t = sh.trk[s];
+        if (sh.new_view[i]) {
+            // rare (a camera sees this track for the first time): one thread appends the new cameras in
+            // camera order and gathers the whole list
+            if (k != 0) continue;
+            PAM_NOUNROLL for (int cam = 0; cam < V; ++cam) {
+                if (sh.t2d[cam][i] < 0 || t.view_slot[cam] >= 0) continue;
+                const int kk = t.nviews++;
+                t.view_cid[kk] = cam; t.view_slot[cam] = (signed char)kk;
+                t.view_time[kk] = frame; t.view_det[kk] = sh.t2d[cam][i];
+            }
+        } else if (k > 0 && k >= t.nviews) {
+            continue;
         }
+        // view k (all views when this thread gathers alone): its place = number of usable views before it
+        const int k0 = sh.new_view[i] ? 0 : k, k1 = sh.new_view[i] ? t.nviews : k + 1;
         int cnt = 0;
         if (t.already) {
-            const int s = sh.hdr.order[i];
-            PAM_NOUNROLL for (int k = 0; k < t.nviews; ++k) {
-                const int age = frame - t.view_time[k];
+            PAM_NOUNROLL for (int kk = 0; kk < k0; ++kk) cnt += (frame - t.view_time[kk] <= c.stale_window) ? 1 : 0;
+            PAM_NOUNROLL for (int kk = k0; kk < k1; ++kk) {
+                const int age = frame - t.view_time[kk];
                 if (age > c.stale_window) continue;
-                const int cam = t.view_cid[k];
+                const int cam = t.view_cid[kk];
                 ViewSrc& vs = sh.vsrc[i * V + cnt++];
                 vs.cid = cam;
                 vs.T = age;
                 // a view matched this frame is read straight from the staged detections
-                const int tl = t.view_time[k] - gin_frame0;    // frame index inside this launch (< 0: earlier launch)
+                const int tl = t.view_time[kk] - gin_frame0;   // frame index inside this launch (< 0: earlier launch)
                 vs.p = (age == 0) ? dets + (int64_t)(cam * D + sh.t2d[cam][i]) * J3
-                     : (tl >= 0) ? gin + ((int64_t)tl * V * D + cam * D + t.view_det[k]) * J3
-                                 : g.view + (int64_t)(s * V + k) * J3;
+                     : (tl >= 0) ? gin + ((int64_t)tl * V * D + cam * D + t.view_det[kk]) * J3
+                                 : g.view + (int64_t)(s * V + kk) * J3;
             }
         }
-        sh.gv_n[i] = cnt;
-        sh.do_update[i] = (t.already && cnt >= 2) ? 1 : 0;
+        if (k1 >= t.nviews) {                        // the thread of the last view closes the list
+            sh.gv_n[i] = cnt;
+            sh.do_update[i] = (t.already && cnt >= 2) ? 1 : 0;
+        }
     }
     PAM_FOR_REV(it, V * D) {
         const int cam = fast_div(it, c.inv_D), d = it - cam * D;
@@ -719,23 +749,32 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         dst[0] = o0; dst[1] = o1; dst[2] = o2;
         g.nv[s * J + j] = sh.nvj[i][j];
         if (j == 0) t.hist_time[pos] = frame;     // no other thread reads this entry in this phase
-        if (track_reported(c, sh, i)) {
-            int k = 0;
-            PAM_NOUNROLL for (int i2 = 0; i2 < i; ++i2) k += track_reported(c, sh, i2) ? 1 : 0;
-            if (out.joints) {
-                float* oj = out.joints + (int64_t)(k * J + j) * 3;
-                oj[0] = (float)o0; oj[1] = (float)o1; oj[2] = (float)o2;
-            }
-            if (out.nviews) out.nviews[k * J + j] = sh.nvj[i][j];
-        }
+        double* keep = sh.raw + (int64_t)(i * J + j) * 3;    // smoothed joint, for the output rows written below
+        keep[0] = o0; keep[1] = o1; keep[2] = o2;
+    }
+    // ... while one otherwise idle thread ranks the tracks that are reported this frame (output row of each)
+    if (ctx.tid() == ctx.nthreads() - 1) {
+        int k = 0;
+        PAM_NOUNROLL for (int i = 0; i < n; ++i) sh.out_row[i] = track_reported(c, sh, i) ? (signed char)(k++) : (signed char)-1;
     }
     ctx.sync();
     PAM_MARK(5);
+    PAM_FOR(it, n * J) {
+        const int i = fast_div(it, c.inv_J), j = it - i * J;
+        const int k = sh.out_row[i];
+        if (k < 0) continue;
+        const double* o = sh.raw + (int64_t)(i * J + j) * 3;
+        if (out.joints) {
+            float* oj = out.joints + (int64_t)(k * J + j) * 3;
+            oj[0] = (float)o[0]; oj[1] = (float)o[1]; oj[2] = (float)o[2];
+        }
+        if (out.nviews) out.nviews[k * J + j] = sh.nvj[i][j];
+    }
 
     // ---- phase 7: life-cycle (IterativeTracker.py:253-274), reported ids, reap (:178), and the
     //      decision whether new-track initialisation has anything to do ---------------------------
     // 7a, one thread per track: counters and state transitions; bit 0 of life_flag = keep, bit 1 = reported
-    PAM_FOR(i, n) {
+    PAM_FOR_REV(i, n) {
         const int s = sh.hdr.order[i];
         TrkMeta& t = sh.trk[s];
         if (sh.do_update[i] && !((double)sh.fail[i] > c.fail_limit) && t.hist_len >= PAM_HIST)
@@ -758,8 +797,8 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         if (t.state != ST_DELETED) flag |= 1;
         sh.life_flag[i] = (signed char)flag;
     }
-    // ... while the last thread decides whether new-track initialisation has anything to do
-    if (ctx.tid() == ctx.nthreads() - 1) {
+    // ... while the thread below them decides whether new-track initialisation has anything to do
+    if (ctx.tid() == (ctx.nthreads() - 1 - n > 0 ? ctx.nthreads() - 1 - n : 0)) {
         int cams_with = 0;
         PAM_NOUNROLL for (int cam = 0; cam < V; ++cam) cams_with += (sh.um_n[cam] > 0);
         // a hypothesis needs views from two cameras to become a track (hypothesis.size() > 1)
