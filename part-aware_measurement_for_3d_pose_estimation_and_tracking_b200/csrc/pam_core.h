@@ -34,9 +34,11 @@
 #if defined(__CUDACC__)
 #define PAM_NOUNROLL _Pragma("unroll 1")
 #define PAM_UNROLL2 _Pragma("unroll 2")
+#define PAM_UNROLL4 _Pragma("unroll 4")
 #else
 #define PAM_NOUNROLL
 #define PAM_UNROLL2
+#define PAM_UNROLL4
 #endif
 
 #define PAM_MAX_V 8        // cameras per rig handled by the stateful tracker

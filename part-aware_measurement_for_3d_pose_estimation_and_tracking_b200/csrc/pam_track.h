@@ -135,6 +135,7 @@ struct SeqShared {
     int gv_n[PAM_MAX_TRK];
     int new_view[PAM_MAX_TRK];               // a matched camera is not in the track's view list yet
     int any_conflict;                        // some camera needs the full assignment solver
+    int any_deleted;                         // a track was deleted this frame: the track list needs compaction
     int do_update[PAM_MAX_TRK];
     int fail[PAM_MAX_TRK];                   // joints left with < 2 views
     int conflict[PAM_MAX_V];                 // camera needs the full assignment solver
@@ -361,7 +362,12 @@ PAM_HD int joint_update(const Team& tm, const DevCfg& c, const SeqShared& sh, in
     PAM_NOUNROLL for (int a = 0; a < Vt; ++a) {
         const double ua = vw.u(a), va = vw.v(a);
         const int ca = vw.cid(a);
-        PAM_NOUNROLL for (int b = a + 1; b < Vt; ++b, ++k) {
+#if defined(PAM_EXP_PAIR2)
+        PAM_UNROLL2
+#else
+        PAM_NOUNROLL
+#endif
+        for (int b = a + 1; b < Vt; ++b, ++k) {
             if (Team::size > 1 && (k & (Team::size - 1)) != tm.rank) continue;   // view pairs are dealt round-robin
             const double ub = vw.u(b), vb = vw.v(b);
             const int cb = vw.cid(b);
@@ -510,7 +516,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         sh.fail[i] = 0;
         sh.new_view[i] = 0;
     }
-    if (ctx.tid() == ctx.nthreads() - 1) sh.any_conflict = 0;
+    if (ctx.tid() == ctx.nthreads() - 1) { sh.any_conflict = 0; sh.any_deleted = 0; }
     PAM_FOR_REV(cc, V) {
         int mm = counts[cc];
         if (mm > D || mm < 0) { sh.hdr.status = SEQ_ERR_DET_OVERFLOW; mm = 0; }
@@ -538,7 +544,12 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         const double inv_denom = sh.inv_denom[i];
         double sum = 0.0;
         int cnt = 0;
-        PAM_UNROLL2 for (int j = 0; j < J; ++j) {     // two joints in flight: the chain per joint is ~20 deep
+#if defined(PAM_EXP_AFF4)
+        PAM_UNROLL4
+#else
+        PAM_UNROLL2
+#endif
+        for (int j = 0; j < J; ++j) {     // two joints in flight: the chain per joint is ~20 deep
             const double x = X[j * 3], y = X[j * 3 + 1], z = X[j * 3 + 2];
             const double iw = rcp_f64(p8 * x + p9 * y + p10 * z + p11);
             const double dv = (p4 * x + p5 * y + p6 * z + p7) * iw - (double)q[j * 3 + 0];
@@ -575,11 +586,11 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         const int mm = sh.m[cam];
         const double* A = sh.aff + (int64_t)(cam * MT) * D;
         int cnt = 0, arg = -1;
-        PAM_NOUNROLL for (int d = 0; d < mm; ++d)
+        PAM_UNROLL4 for (int d = 0; d < mm; ++d)           // independent loads: four in flight
             if (A[i * D + d] > 0.0) { ++cnt; arg = d; }
         if (cnt == 1) {
             int col = 0;
-            PAM_NOUNROLL for (int k = 0; k < n; ++k) col += (A[k * D + arg] > 0.0) ? 1 : 0;
+            PAM_UNROLL4 for (int k = 0; k < n; ++k) col += (A[k * D + arg] > 0.0) ? 1 : 0;
             if (col == 1) {
                 sh.t2d[cam][i] = (signed char)arg; sh.d2t[cam][arg] = (signed char)i;
                 apply_match(i, cam, arg);
@@ -756,6 +767,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
     if (ctx.tid() == ctx.nthreads() - 1) {
         int k = 0;
         PAM_NOUNROLL for (int i = 0; i < n; ++i) sh.out_row[i] = track_reported(c, sh, i) ? (signed char)(k++) : (signed char)-1;
+        if (out.count) *out.count = k;
     }
     ctx.sync();
     PAM_MARK(5);
@@ -794,7 +806,8 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
             if (t.state == ST_TENTATIVE && !t.already) t.state = ST_DELETED;
             else if (t.tsu >= c.max_age) t.state = ST_DELETED;
         }
-        if (t.state != ST_DELETED) flag |= 1;
+        if (t.state != ST_DELETED) flag |= 1; else sh.any_deleted = 1;
+        if ((flag & 2) && out.ids) out.ids[sh.out_row[i]] = t.track_id;     // reported <=> out_row >= 0
         sh.life_flag[i] = (signed char)flag;
     }
     // ... while the thread below them decides whether new-track initialisation has anything to do
@@ -812,28 +825,24 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         }
     }
     ctx.sync();
-    // 7b, one thread: reported ids in track order, compaction of the track list
+    // 7b, one thread: compaction of the track list, only on the frames a track was deleted
     if (ctx.tid() == 0) {
-        int k = 0, wr = 0;
-        PAM_NOUNROLL for (int i = 0; i < n; ++i) {
-            const int s = sh.hdr.order[i];
-            const int flag = sh.life_flag[i];
-            if (flag & 2) {
-                if (out.ids) out.ids[k] = sh.trk[s].track_id;
-                ++k;
+        if (sh.any_deleted) {
+            int wr = 0;
+            PAM_NOUNROLL for (int i = 0; i < n; ++i) {
+                const int s = sh.hdr.order[i];
+                if (sh.life_flag[i] & 1) sh.hdr.order[wr++] = s;
+                else sh.hdr.used_mask &= ~(1u << s);
             }
-            if (flag & 1) sh.hdr.order[wr++] = s;
-            else sh.hdr.used_mask &= ~(1u << s);
+            sh.hdr.ntracks = wr;
         }
-        sh.hdr.ntracks = wr;
         sh.hdr.frames_done += 1;
-        if (out.count) *out.count = k;
     }
-    ctx.sync();
     PAM_MARK(6);
 
     // ---- phase 8: new-track initialisation (IterativeTracker.py:52-113); rare in steady state ---
-    if (sh.do_init) {
+    if (sh.do_init) {          // uniform: written before the last barrier
+        ctx.sync();            // the track list of 7b is read (and extended) below
         // grow hypotheses camera by camera
         PAM_NOUNROLL for (int cam = 1; cam < V; ++cam) {
             const int nh = sh.hyp_n, nd = sh.um_n[cam];
