@@ -35,10 +35,13 @@
 #define PAM_NOUNROLL _Pragma("unroll 1")
 #define PAM_UNROLL2 _Pragma("unroll 2")
 #define PAM_UNROLL4 _Pragma("unroll 4")
+#define PAM_PRAGMA_(x) _Pragma(#x)
+#define PAM_UNROLL_N(n) PAM_PRAGMA_(unroll (n))
 #else
 #define PAM_NOUNROLL
 #define PAM_UNROLL2
 #define PAM_UNROLL4
+#define PAM_UNROLL_N(n)
 #endif
 
 #define PAM_MAX_V 8        // cameras per rig handled by the stateful tracker

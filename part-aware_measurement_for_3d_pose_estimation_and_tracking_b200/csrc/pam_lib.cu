@@ -20,7 +20,9 @@ using namespace pam;
 // ----------------------------------------------------------------------------------------------
 // persistent per-sequence tracker kernel: one CTA owns one sequence for all T frames
 // ----------------------------------------------------------------------------------------------
-struct DeviceCtx {
+template <int AFF_UNROLL>
+struct DeviceCtxT {
+    static constexpr int kAffinityUnroll = AFF_UNROLL;
     __host__ __device__ __forceinline__ int tid() const {
 #ifdef __CUDA_ARCH__
         return threadIdx.x;
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
 k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, int T, int frame0, const TrackIO io) {
     extern __shared__ double arena[];
     __shared__ SeqShared sh;
-    DeviceCtx ctx;
+    DeviceCtxT<(MAXT * MINB <= 512) ? 4 : 2> ctx;     // <= 512 resident threads per SM: 128 registers each
     const int s = blockIdx.x;
     SeqGlobal g;
     g.bind(c, state + (int64_t)s * c.seq_bytes);
@@ -189,6 +191,9 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
         for (int k = 0; k < 9; ++k) tot += sh.phase_cyc[k];
         for (int k = 0; k < 9; ++k)
             printf("phase %-22s %9.0f cyc/frame %5.1f%%\n", nm[k], (double)sh.phase_cyc[k] / T, 100.0 * sh.phase_cyc[k] / tot);
+        static const char* sub[4] = {"5a pair tests", "5b conflict resolution", "5c gram fold", "5d solve"};
+        for (int k = 0; k < 4; ++k)   // thread 0's item; the remainder of phase 5 (stores, barrier wait) stays in its row above
+            printf("  sub %-22s %9.0f cyc/frame\n", sub[k], (double)sh.phase_cyc[10 + k] / T);
         printf("total %.0f cyc/frame\n", (double)tot / T);
     }
 #endif

@@ -133,7 +133,7 @@ struct SeqShared {
     signed char d2t[PAM_MAX_V][PAM_MAX_D];
     ViewSrc* vsrc;    // [max_trk][V]         (arena) gathered views per track, dict order
     int gv_n[PAM_MAX_TRK];
-    int new_view[PAM_MAX_TRK];               // a matched camera is not in the track's view list yet
+    signed char new_view[PAM_MAX_TRK];       // a matched camera is not in the track's view list yet
     int any_conflict;                        // some camera needs the full assignment solver
     int any_deleted;                         // a track was deleted this frame: the track list needs compaction
     int do_update[PAM_MAX_TRK];
@@ -194,6 +194,7 @@ PAM_HD void carve(const DevCfg& c, SeqShared& sh, double* arena, const SeqGlobal
 }
 
 struct HostCtx {
+    static constexpr int kAffinityUnroll = 1;
     inline int tid() const { return 0; }
     inline int nthreads() const { return 1; }
     inline void sync() const {}
@@ -210,8 +211,19 @@ struct HostCtx {
             sh.tlast = _t;                                                 \
         }                                                                  \
     } while (0)
+// finer marks inside the per-joint functions of phase 5 (thread 0's item; `sh` is a const reference there)
+#define PAM_SUBMARK(k)                                                     \
+    do {                                                                   \
+        if (threadIdx.x == 0) {                                            \
+            SeqShared& _m = const_cast<SeqShared&>(sh);                    \
+            long long _t = clock64();                                      \
+            _m.phase_cyc[k] += _t - _m.tlast;                              \
+            _m.tlast = _t;                                                 \
+        }                                                                  \
+    } while (0)
 #else
 #define PAM_MARK(k) do { } while (0)
+#define PAM_SUBMARK(k) do { } while (0)
 #endif
 
 // A "team" = W adjacent lanes that cooperate on one (track, joint) item in phase 5: they split the
@@ -335,6 +347,7 @@ PAM_HD void dlt_from_views(const Team& tm, const SeqShared& sh, int Vt, const Vi
     acc.reset(true);
     PAM_NOUNROLL for (int a = tm.rank; a < Vt; a += Team::size)
         if ((alive >> a) & 1u) acc.add_view(sh.Pc(vw.cid(a)), vw.u(a), vw.v(a), vw.w(a));
+    PAM_SUBMARK(12);
     if (Team::size > 1) {     // the Gram matrix is additive over views
         acc.r00 = tm.sum_f64(acc.r00); acc.r01 = tm.sum_f64(acc.r01); acc.r02 = tm.sum_f64(acc.r02);
         acc.r03 = tm.sum_f64(acc.r03); acc.r11 = tm.sum_f64(acc.r11); acc.r12 = tm.sum_f64(acc.r12);
@@ -342,6 +355,7 @@ PAM_HD void dlt_from_views(const Team& tm, const SeqShared& sh, int Vt, const Vi
         acc.r33 = tm.sum_f64(acc.r33);
     }
     acc.solve(X, &path);
+    PAM_SUBMARK(13);
     if (path < 0) {
         acc.reset(false);
         PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
@@ -362,12 +376,7 @@ PAM_HD int joint_update(const Team& tm, const DevCfg& c, const SeqShared& sh, in
     PAM_NOUNROLL for (int a = 0; a < Vt; ++a) {
         const double ua = vw.u(a), va = vw.v(a);
         const int ca = vw.cid(a);
-#if defined(PAM_EXP_PAIR2)
-        PAM_UNROLL2
-#else
-        PAM_NOUNROLL
-#endif
-        for (int b = a + 1; b < Vt; ++b, ++k) {
+        PAM_NOUNROLL for (int b = a + 1; b < Vt; ++b, ++k) {
             if (Team::size > 1 && (k & (Team::size - 1)) != tm.rank) continue;   // view pairs are dealt round-robin
             const double ub = vw.u(b), vb = vw.v(b);
             const int cb = vw.cid(b);
@@ -387,6 +396,7 @@ PAM_HD int joint_update(const Team& tm, const DevCfg& c, const SeqShared& sh, in
         const uint32_t lo = tm.or_u32((uint32_t)conflict), hi = tm.or_u32((uint32_t)(conflict >> 32));
         conflict = ((uint64_t)hi << 32) | lo;
     }
+    PAM_SUBMARK(10);
     uint32_t alive = (1u << Vt) - 1u;
     if (conflict) {                // identical on every lane of the team; rare, so the ray distances are
         PAM_NOUNROLL for (int a = 0; a < Vt; ++a)                     // simply recomputed per conflict
@@ -398,6 +408,7 @@ PAM_HD int joint_update(const Team& tm, const DevCfg& c, const SeqShared& sh, in
                 if (ra > rb) alive &= ~(1u << a); else alive &= ~(1u << b);
             }
     }
+    PAM_SUBMARK(11);
     const int nv = popcount32(alive);
     if (nv < 2) {
         X[0] = next[0]; X[1] = next[1]; X[2] = next[2];
@@ -544,12 +555,9 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         const double inv_denom = sh.inv_denom[i];
         double sum = 0.0;
         int cnt = 0;
-#if defined(PAM_EXP_AFF4)
-        PAM_UNROLL4
-#else
-        PAM_UNROLL2
-#endif
-        for (int j = 0; j < J; ++j) {     // two joints in flight: the chain per joint is ~20 deep
+        // joints in flight per thread (the chain per joint is ~20 deep): 2 in the register-lean variants,
+        // 4 where the launch shape leaves the full register budget (single streams)
+        PAM_UNROLL_N(Ctx::kAffinityUnroll) for (int j = 0; j < J; ++j) {
             const double x = X[j * 3], y = X[j * 3 + 1], z = X[j * 3 + 2];
             const double iw = rcp_f64(p8 * x + p9 * y + p10 * z + p11);
             const double dv = (p4 * x + p5 * y + p6 * z + p7) * iw - (double)q[j * 3 + 0];
