@@ -48,6 +48,7 @@
 #define PAM_MAX_TRK 16     // track slots per sequence
 #define PAM_MAX_D 16       // detections per camera per frame
 #define PAM_MAX_J 32       // joints
+#define PAM_RECENT 5       // newest history entries the smoothing / velocity step keeps in registers
 #define PAM_MAX_HYP 32     // person hypotheses during new-track initialisation
 #define PAM_HIST 12        // smoothed-pose history ring (max_age + 2 <= PAM_HIST)
 #define PAM_MAX_RADIUS 8   // Gaussian radius int(4 sigma + 0.5)

@@ -191,8 +191,9 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
         for (int k = 0; k < 9; ++k) tot += sh.phase_cyc[k];
         for (int k = 0; k < 9; ++k)
             printf("phase %-22s %9.0f cyc/frame %5.1f%%\n", nm[k], (double)sh.phase_cyc[k] / T, 100.0 * sh.phase_cyc[k] / tot);
-        static const char* sub[4] = {"5a pair tests", "5b conflict resolution", "5c gram fold", "5d solve"};
-        for (int k = 0; k < 4; ++k)   // thread 0's item; the remainder of phase 5 (stores, barrier wait) stays in its row above
+        static const char* sub[7] = {"5a pair tests", "5b conflict resolution", "5c gram fold", "5d solve",
+                                     "6a prologue", "6b smoothing", "6c velocity"};
+        for (int k = 0; k < 7; ++k)   // thread 0's item; the remainder of phase 5 (stores, barrier wait) stays in its row above
             printf("  sub %-22s %9.0f cyc/frame\n", sub[k], (double)sh.phase_cyc[10 + k] / T);
         printf("total %.0f cyc/frame\n", (double)tot / T);
     }

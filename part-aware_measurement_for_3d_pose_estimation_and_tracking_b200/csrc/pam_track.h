@@ -739,31 +739,77 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, SeqShared& sh, const SeqGlobal
         const double* raw = sh.raw + (int64_t)(i * J + j) * 3;
         const double* hb = g.hist + ((int64_t)(s * PAM_HIST) * J + j) * 3;   // + ring * J3
         double o0 = raw[0] * w[0], o1 = raw[1] * w[0], o2 = raw[2] * w[0];
-        PAM_NOUNROLL for (int k = rad; k >= 1; --k) {
-            const int il = reflect_index(L - k, N), ir = reflect_index(L + k, N);
-            const double* xl = (il == L) ? raw : hb + (int64_t)((start + il) % PAM_HIST) * J3;
-            const double* xr = (ir == L) ? raw : hb + (int64_t)((start + ir) % PAM_HIST) * J3;
-            o0 += (xl[0] + xr[0]) * w[k];
-            o1 += (xl[1] + xr[1]) * w[k];
-            o2 += (xl[2] + xr[2]) * w[k];
-        }
+        PAM_MARK(14);
         // window after the append and the at-most-one-entry trim (IterativeTracker.py:330-332)
         int len2 = L + 1, start2 = start;
         if (frame - t.hist_time[start] > c.max_age) { start2 = (start + 1) % PAM_HIST; len2 -= 1; }
-        if (len2 >= 2) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-            float h0 = (float)o0, h1 = (float)o1, h2 = (float)o2;    // newest entry = this frame's pose
-            int cnt = 0;
-            PAM_NOUNROLL for (int idx = len2 - 1; idx >= 1 && cnt < 5; --idx, ++cnt) {
-                const double* lo = hb + (int64_t)((start2 + idx - 1) % PAM_HIST) * J3;
-                const float l0 = (float)lo[0], l1 = (float)lo[1], l2 = (float)lo[2];
-                a0 += h0 - l0; a1 += h1 - l1; a2 += h2 - l2;
-                h0 = l0; h1 = l1; h2 = l2;
+        float* vel = g.vel + (int64_t)(s * J + j) * 3;
+#if !defined(PAM_NO_HIST_PRELOAD)
+        if (rad <= PAM_RECENT && rad <= L) {
+            // Steady state.  Both the Gaussian (samples L-rad .. L, each history sample used twice by the
+            // reflection at the end of the series) and the velocity (last <= 5 differences) read the newest
+            // history entries: they are fetched once, all loads in flight together -- the ring was written
+            // by this CTA's own global stores, so every dependent load would pay an L2 round trip.
+            double hx[PAM_RECENT][3];
+#pragma unroll
+            for (int q = 0; q < PAM_RECENT; ++q) {
+                const int e = (q < L) ? L - 1 - q : 0;                       // clamped: never used beyond L
+                const double* x = hb + (int64_t)((start + e) % PAM_HIST) * J3;
+                hx[q][0] = x[0]; hx[q][1] = x[1]; hx[q][2] = x[2];
             }
-            float* vel = g.vel + (int64_t)(s * J + j) * 3;
-            const float fc = (float)cnt;
-            vel[0] = a0 / fc; vel[1] = a1 / fc; vel[2] = a2 / fc;
+#pragma unroll
+            for (int k = PAM_RECENT; k >= 1; --k) {                          // same order as the generic loop
+                if (k > rad) continue;
+                // sample L-k and its mirror partner L-k+1 (the current raw pose for k = 1)
+                const double r0 = (k == 1) ? raw[0] : hx[k >= 2 ? k - 2 : 0][0];
+                const double r1 = (k == 1) ? raw[1] : hx[k >= 2 ? k - 2 : 0][1];
+                const double r2 = (k == 1) ? raw[2] : hx[k >= 2 ? k - 2 : 0][2];
+                o0 += (hx[k - 1][0] + r0) * w[k];
+                o1 += (hx[k - 1][1] + r1) * w[k];
+                o2 += (hx[k - 1][2] + r2) * w[k];
+            }
+            PAM_MARK(15);
+            if (len2 >= 2) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+                float h0 = (float)o0, h1 = (float)o1, h2 = (float)o2;    // newest entry = this frame's pose
+                const int cnt = (len2 - 1 < 5) ? len2 - 1 : 5;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    if (q >= cnt) continue;
+                    const float l0 = (float)hx[q][0], l1 = (float)hx[q][1], l2 = (float)hx[q][2];
+                    a0 += h0 - l0; a1 += h1 - l1; a2 += h2 - l2;
+                    h0 = l0; h1 = l1; h2 = l2;
+                }
+                const float fc = (float)cnt;
+                vel[0] = a0 / fc; vel[1] = a1 / fc; vel[2] = a2 / fc;
+            }
+        } else
+#endif
+        {
+            PAM_NOUNROLL for (int k = rad; k >= 1; --k) {
+                const int il = reflect_index(L - k, N), ir = reflect_index(L + k, N);
+                const double* xl = (il == L) ? raw : hb + (int64_t)((start + il) % PAM_HIST) * J3;
+                const double* xr = (ir == L) ? raw : hb + (int64_t)((start + ir) % PAM_HIST) * J3;
+                o0 += (xl[0] + xr[0]) * w[k];
+                o1 += (xl[1] + xr[1]) * w[k];
+                o2 += (xl[2] + xr[2]) * w[k];
+            }
+            PAM_MARK(15);
+            if (len2 >= 2) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+                float h0 = (float)o0, h1 = (float)o1, h2 = (float)o2;    // newest entry = this frame's pose
+                int cnt = 0;
+                PAM_NOUNROLL for (int idx = len2 - 1; idx >= 1 && cnt < 5; --idx, ++cnt) {
+                    const double* lo = hb + (int64_t)((start2 + idx - 1) % PAM_HIST) * J3;
+                    const float l0 = (float)lo[0], l1 = (float)lo[1], l2 = (float)lo[2];
+                    a0 += h0 - l0; a1 += h1 - l1; a2 += h2 - l2;
+                    h0 = l0; h1 = l1; h2 = l2;
+                }
+                const float fc = (float)cnt;
+                vel[0] = a0 / fc; vel[1] = a1 / fc; vel[2] = a2 / fc;
+            }
         }
+        PAM_MARK(16);
         double* dst = g.hist + ((int64_t)(s * PAM_HIST + pos) * J + j) * 3;
         dst[0] = o0; dst[1] = o1; dst[2] = o2;
         g.nv[s * J + j] = sh.nvj[i][j];
