@@ -40,6 +40,12 @@ SHAPE = "shelf"
 METRIC = "synthetic multi-view frames/sec (triangulated+associated)"
 
 
+def workload_name(shape_name, sh, T, S):
+    """The workload both arms are quoted on (config.workload)."""
+    return (f"{shape_name}: {sh.V} cameras x {sh.P} people x {sh.J} joints x {T} frames, {S} independent "
+            f"sequences per GPU")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -206,8 +212,8 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * frames * cores / val, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{a.shape}: {sh.V} cameras x {sh.P} people x {sh.J} joints, {cores} sequences x "
-                               f"{frames} frames per step (bounded sample of the {sh.T}-frame streams)"},
+        "config": {"workload": workload_name(a.shape, sh, a.frames or sh.T, a.sequences),
+                   "sample": f"each step: {cores} sequences x {frames} frames of that workload, one process per host core"},
         "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{cores} processes x {frames} frames, numpy oracle (bit-identical restatement of "
                                    "the reference's IterativeTracker.tracking), timer around tracking() only"},
@@ -412,8 +418,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{a.shape}: {V} cameras x {sh.P} people x {J} joints x {T} frames, {S} independent "
-                               f"sequences per GPU", "sequences_per_gpu": S, "frames": T, "max_tracks": MT,
+        "config": {"workload": workload_name(a.shape, sh, T, S), "sequences_per_gpu": S, "frames": T, "max_tracks": MT,
                    "l2": f"inputs larger than L2 ({d_dets.numel() * 4 / 1e9:.2f} GB of detections per GPU per step)",
                    "gen_seconds": round(gen_s, 1), "cpus_bound_per_rank": numa_cpus, "reports_per_step": int(counters[0].item()),
                    "pcp_percent": (round(100.0 * counters[2].item() / max(1, counters[3].item()), 3) if do_eval else None),
