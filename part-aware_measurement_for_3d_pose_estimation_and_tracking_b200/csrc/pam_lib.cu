@@ -364,7 +364,7 @@ typedef void (*track_kernel_t)(const DevCfg, const CamConst, char*, int, int, co
 // register budget variants: <= 128 threads with 4 / 6 / 8 CTAs per SM, or up to 256 threads
 // Launch shape per call.  Few sequences: latency matters -- one CTA per sequence with the full register
 // budget.  Many sequences: the kernel is latency/barrier bound, so more, smaller CTAs per SM win
-// (measured on B200, Shelf shape: 128 thr x 4/SM 27 M frames/s, 128 x 6 33 M, 128 x 8 38 M, 64 x 12 40 M).
+// (measured on B200, Shelf shape, final kernel: 128 thr x 8/SM 57 M frames/s, 96 x 8 59 M, 64 x 12 59 M at 12 per SM).
 // Two lanes per (track, joint) (PAM_TRACK_TEAM=2) measured no faster than one, so 1 is the default.
 static track_kernel_t pick_track_kernel(const pam_handle* h, int S, int* threads) {
     const int per_sm = (S + h->num_sms - 1) / h->num_sms;
@@ -372,6 +372,9 @@ static track_kernel_t pick_track_kernel(const pam_handle* h, int S, int* threads
     int nt = h->track_threads;                       // PAM_TRACK_THREADS or the size-based default
     int mb = h->track_minblocks;
     if (!h->threads_forced && nt <= 128 && team == 1 && !mb && per_sm >= 10) nt = 64;
+    // 7-9 sequences per SM: three warps per CTA (the fourth one of a 128-thread CTA has nothing to do in any
+    // phase of the usual shapes) leave 80 registers per thread at 8 CTAs per SM: 59 M against 57 M frames/s
+    if (!h->threads_forced && nt == 128 && team == 1 && !mb && per_sm >= 7 && per_sm < 10) nt = 96;
     if (!mb) mb = nt > 128 ? (per_sm > 2 ? 4 : 2) : (nt <= 64 && per_sm >= 10 ? 12 : (per_sm >= 7 ? 8 : (per_sm > 4 ? 6 : 4)));
     *threads = nt;
     if (nt > 128) {
@@ -379,6 +382,7 @@ static track_kernel_t pick_track_kernel(const pam_handle* h, int S, int* threads
         return mb >= 4 ? k_track_sequences<256, 4, 1> : k_track_sequences<256, 2, 1>;
     }
     if (team > 1) return mb >= 6 ? k_track_sequences<128, 6, 2> : k_track_sequences<128, 4, 2>;
+    if (nt == 96 && team == 1) return k_track_sequences<96, 8, 1>;     // three warps, 85 registers, 8 CTAs per SM
     if (nt <= 64 && mb >= 10) return mb >= 12 ? k_track_sequences<64, 12, 1> : k_track_sequences<64, 10, 1>;
     switch (mb) {
         case 8: case 10: case 12: return k_track_sequences<128, 8, 1>;

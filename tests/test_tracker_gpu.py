@@ -110,3 +110,28 @@ def test_capacity_overflow_is_reported():
     with pytest.raises(tracker.PamError) as e:
         trk.check()
     assert "capacity" in str(e.value)
+
+
+@pytest.mark.parametrize("env", [
+    {"PAM_TRACK_THREADS": "96"},                                   # 3 warps x 8 CTAs/SM (default at 7-9 sequences per SM)
+    {"PAM_TRACK_THREADS": "64", "PAM_TRACK_MINBLOCKS": "12"},      # 2 warps x 12 CTAs/SM (default at >= 10 per SM)
+    {"PAM_TRACK_THREADS": "128", "PAM_TRACK_MINBLOCKS": "8"},      # 4 warps x 8 CTAs/SM, 64 registers
+    {"PAM_TRACK_THREADS": "256"},
+    {"PAM_TRACK_THREADS": "256", "PAM_TRACK_TEAM": "2"},           # two lanes per (track, joint)
+])
+def test_every_launch_shape_matches_oracle(env, monkeypatch):
+    """The launch shape is picked from the batch size; small test batches only ever see the single-stream
+    shape, so every other register / CTA-size variant is forced here (read at pam_create) and checked."""
+    import torch
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    streams = [synth.make_stream("shelf", 40 + s, 150, miss_prob=0.08, outlier_prob=0.04, enter_stagger=10 * s) for s in range(3)]
+    trk = _tracker_for(streams)
+    dets = torch.from_numpy(np.stack([st.dets for st in streams])).cuda()
+    counts = torch.from_numpy(np.stack([st.counts for st in streams])).cuda()
+    out = trk.run(dets, counts, nviews=True, assoc=True)
+    assert trk.check().tolist() == [0, 0, 0]
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    for s, st in enumerate(streams):
+        oo, oa, _ = util.run_oracle(st)
+        util.compare_with_oracle(out, s, st, oo, oa)
