@@ -63,6 +63,18 @@ extern "C" int hostemu_state_layout(const pam_config* cfg, pam_state_layout* L) 
     return PAM_OK;
 }
 
+// the building blocks below phase level, one at a time (tests/test_primitives_hostemu.py)
+extern "C" int hostemu_lsap(int nr, int nc, const double* cost /*[nr][nc]*/, int* col4row /*[nr]*/) {
+    return pam::lsap_solve<64>(nr, nc, [&](int i, int j) { return cost[i * nc + j]; }, col4row);
+}
+extern "C" int hostemu_gaussian_weights(double sigma, double* w /*[PAM_MAX_RADIUS + 1]*/) { return pam::gaussian_weights(sigma, w); }
+extern "C" int hostemu_reflect_index(int i, int n) { return pam::reflect_index(i, n); }
+extern "C" double hostemu_np_sum(const double* x, int n) { return pam::np_sum(x, n); }
+extern "C" double hostemu_mean_confidence(const float* pose /*[J][3]*/, int J) { return pam::mean_confidence(pose, J); }
+extern "C" double hostemu_sqrt(double x) { return pam::sqrt_f64(x); }
+extern "C" double hostemu_rsqrt(double x) { return pam::rsqrt_f64(x); }
+extern "C" double hostemu_rcp(double x) { return pam::rcp_f64(x); }
+
 // DLT extractor check: n joints, V views each; mode 0 = product policy (Gram when all weights are 1),
 // 1 = force Givens + inverse iteration/Jacobi, 2 = force Givens + Jacobi only.
 extern "C" int hostemu_dlt(int n, int V, const double* P, const double* uv, const double* w, const uint8_t* keep,
