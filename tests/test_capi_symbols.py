@@ -51,3 +51,21 @@ def test_create_fails_loudly_without_device_or_on_bad_config():
         ok = _capi.make_config(prm, 5, 4, 8)
         assert lib.pam_create(C.byref(ok), 0, C.byref(h)) == -2       # PAM_E_CUDA: no CPU fallback
         assert b"no usable CUDA device" in lib.pam_last_error(None)
+
+
+def test_library_is_sm100a_and_stages_frames_with_tma():
+    """Static evidence from the built library (no GPU needed): the only embedded cubin is sm_100a, and the
+    tracker kernel stages detections with a TMA bulk copy completed on an mbarrier (UBLKCP / SYNCS in SASS)."""
+    import shutil
+    import subprocess
+    from pam_b200 import _capi
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    elfs = subprocess.run([cuobjdump, "-lelf", _capi.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", elfs))
+    assert archs == {"sm_100a"}, elfs
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_Z17k_track_sequencesILi128ELi4ELi1EEvN3pam6DevCfgENS0_8CamConstEPcii7TrackIO",
+                           _capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass and "SYNCS" in sass
+    assert "DFMA" in sass and "MUFU.RSQ64H" in sass        # FP64 path with the short MUFU-seeded reciprocal square root
