@@ -81,3 +81,19 @@ def test_random_large_configuration(seed):
     assert out["status"].tolist() == [0]
     oo, oa, _ = generic.run_stream(st, params, shape.arm_joints, min_valid, trace=True)
     util.compare_with_oracle(out, 0, st, oo, oa)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [89, 91])     # V8 D5 J32 and V6 D8 J30: > 48 KB of dynamic shared memory per CTA
+def test_random_large_configuration_gpu(seed):
+    import torch
+    from pam_b200 import camera, tracker
+    shape, params, kw, min_valid = _large_case(seed)
+    st = synth.make_stream(shape, seed, shape.T, rig=synth.make_rig(shape), **kw)
+    trk = tracker.SequenceTracker(camera.GetCameraParameters(st.rig), params, 1, max_detections=st.dets.shape[2],
+                                  max_tracks=16, arm_joints=shape.arm_joints, min_valid_joints=min_valid)
+    out = trk.run(torch.from_numpy(st.dets[None]).cuda(), torch.from_numpy(st.counts[None]).cuda(), nviews=True, assoc=True)
+    assert trk.check().tolist() == [0]
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    oo, oa, _ = generic.run_stream(st, params, shape.arm_joints, min_valid, trace=True)
+    util.compare_with_oracle(out, 0, st, oo, oa)
