@@ -28,11 +28,12 @@
 extern "C" {
 #endif
 
-#define PAM_ABI_VERSION 1
+#define PAM_ABI_VERSION 2
 
-/* compile-time capacity limits of the stateful tracker (pam_core.h) */
+/* capacity limits of the stateful tracker (pam_core.h).  Tracks / detections / joints / cameras are run-time
+ * values of pam_config below these bounds: the working set of a sequence is sized from them. */
 #define PAM_LIMIT_CAMERAS 8        /* stateful tracker; stateless ops: 32 */
-#define PAM_LIMIT_TRACKS 16
+#define PAM_LIMIT_TRACKS 32
 #define PAM_LIMIT_DETECTIONS 16
 #define PAM_LIMIT_JOINTS 32
 
@@ -41,7 +42,8 @@ typedef enum pam_status {
     PAM_E_INVALID = -1,        /* bad argument / configuration outside the limits above          */
     PAM_E_CUDA = -2,           /* a CUDA runtime call failed (no device, out of memory, ...)      */
     PAM_E_NOCAMERAS = -3,      /* pam_set_cameras has not been called                              */
-    PAM_E_CAPACITY = -4,       /* a sequence exceeded max_tracks / hypotheses / max_detections     */
+    PAM_E_CAPACITY = -4,       /* a sequence exceeded max_tracks / hypotheses / max_detections: the excess
+                                  was DROPPED for that frame and tracking went on (pam_track_status) */
     PAM_E_INTERNAL = -5
 } pam_status;
 
@@ -74,21 +76,25 @@ typedef struct pam_config {
  * code can read tracks back (IterTrack read surface, tracking/IterativeTracker.py:194-204). */
 typedef struct pam_state_layout {
     int64_t seq_bytes;          /* stride between sequences                                         */
-    int64_t off_header;         /* int32: ntracks, next_id, status, frames_done, used_mask, order[16] */
+    int64_t off_header;         /* int32 x header_ints: ntracks, next_id, status, frames_done, used_mask,
+                                   warn (PAM_WARN_* bits), warn_frames, reserved; then int8 order[max_order] */
     int64_t off_meta;           /* per slot, int32 x meta_ints                                      */
-    int64_t off_hist;           /* double [slot][hist_len][J][3]  smoothed pose ring                */
+    int64_t off_hist;           /* double [slot][hist_ring][J][3]  smoothed pose ring               */
     int64_t off_view;           /* float  [slot][V][J][3]         last (v,u,conf) per view slot;
                                    written at the END of every launch (inside a launch stale views
                                    are read from the launch's own detection tensor)               */
     int64_t off_vel;            /* float  [slot][J][3]            velocity                          */
     int64_t off_nviews;         /* uint8  [slot][J]               views used for the last pose      */
+    int64_t off_margin;         /* double [n_margins]  decision margins (PAM_MARGIN builds only)    */
     int32_t meta_ints;          /* ints per slot: id,hits,age,tsu,state,already,nviews,hist_start,
                                    hist_len, view_cid[8], view_time[8], hist_time[hist_ring],
                                    then 8 bytes camera -> view-slot map and 8 bytes
                                    detection index of each view inside its own frame             */
     int32_t hist_ring;          /* ring length                                                      */
     int32_t max_views;          /* 8                                                                */
-    int32_t max_order;          /* 16                                                               */
+    int32_t max_order;          /* 32                                                               */
+    int32_t header_ints;        /* 8                                                                */
+    int32_t n_margins;          /* 8                                                                */
 } pam_state_layout;
 
 typedef struct pam_handle pam_handle;
@@ -114,29 +120,58 @@ int pam_get_state_layout(const pam_handle* h, pam_state_layout* out);
 /* track_restart (tracking/IterativeTracker.py:47-50) for S sequences: d_state = S * seq_bytes. */
 int pam_track_reset(pam_handle* h, void* d_state, int32_t S, void* stream);
 
-/* Run T consecutive frames (frame ids frame0 .. frame0+T-1) of S independent sequences, one CTA
- * per sequence, no host involvement between frames.
+/* Run T consecutive frames (frame ids frame0 .. frame0+T-1) of S independent sequences with no host
+ * involvement between frames.  One thread group (1-8 warps, chosen from S) owns one sequence; several
+ * groups share a CTA and its camera constants.
  *   d_dets   [S][T][V][D][J][3] f32 (v,u,conf), zero padded        d_counts [S][T][V] i32
  *   d_out_count [S][T] i32   number of reported tracks (Confirmed and updated this frame,
  *                            ivclabpose.py:265-267), in track-list order
  *   d_out_ids   [S][T][max_tracks] i32          d_out_joints [S][T][max_tracks][J][3] f32
  *   d_out_nviews [S][T][max_tracks][J] u8 (may be NULL)  views each joint was built from
- *   d_out_assoc  [S][T][V][D] i32 (may be NULL) track id matched to each detection, -1 = none */
+ *   d_out_assoc  [S][T][V][D] i32 (may be NULL) track id matched to each detection, -1 = none
+ *   d_out_timing [S][T][4] i32 (may be NULL) SM cycles of the frame: association (affinity + assignment),
+ *                update, initialisation, total -- the (asso_time, update_time, init_time) tuple
+ *                tracking() returns (tracking/IterativeTracker.py:131,169-180); pam_sm_clock_khz converts */
 int pam_track_sequences(pam_handle* h, void* d_state, int32_t S, int32_t T, int32_t frame0,
                         const float* d_dets, const int32_t* d_counts, int32_t* d_out_count,
                         int32_t* d_out_ids, float* d_out_joints, uint8_t* d_out_nviews,
-                        int32_t* d_out_assoc, void* stream);
+                        int32_t* d_out_assoc, int32_t* d_out_timing, void* stream);
 
-/* Per-sequence status words (0 = ok, >0 = capacity error code); synchronises `stream`.
- * Returns PAM_E_CAPACITY if any sequence is in error. */
+/* Per-sequence status words; synchronises `stream`.  h_status[s] (may be NULL) = hard error code
+ * (0 = ok) | PAM_WARN_* bits << 8.  The reference has no capacity limits; here a frame that needs more
+ * track slots / hypotheses / detections than configured DROPS the excess (the new track is not created,
+ * the detection is ignored), tracking continues, and the sequence is flagged.  Returns PAM_E_CAPACITY if
+ * any sequence carries a warning, PAM_E_INTERNAL for a hard error, else PAM_OK. */
+#define PAM_WARN_TRACKS 1
+#define PAM_WARN_HYPOTHESES 2
+#define PAM_WARN_DETECTIONS 4
 int pam_track_status(pam_handle* h, const void* d_state, int32_t S, int32_t* h_status, void* stream);
 
+/* Decision margins of a run (libraries built with -DPAM_MARGIN only, else PAM_E_INVALID): for every
+ * sequence n_margins doubles = the smallest distance any decision came to flipping since the last reset:
+ * |c| of "c > 0" (IterativeTracker.py:143), |A| of "A < 0" (matching.py:248), |ra-rb|/max of the ray rule
+ * (matching.py:272), |believe - conf_threshold| (IterativeTracker.py:59), init-mode |A| (f32) and row-sum
+ * difference (matching.py:287-294), |cost - 1| of the veto (hypothesis.py:66), smallest positive affinity. */
+int pam_track_margins(pam_handle* h, const void* d_state, int32_t S, double* h_margins, void* stream);
+
+/* Launch shape the tracker would use for S sequences: out[0] = warps per sequence, [1] = sequences per
+ * CTA, [2] = threads per CTA, [3] = resident CTAs per SM, [4] = dynamic shared memory per CTA (bytes),
+ * [5] = registers per thread, [6] = working-set bytes per sequence, [7] = detection buffers per sequence. */
+int pam_track_launch_info(pam_handle* h, int32_t S, int32_t* out8);
+
+/* SM clock (kHz) the cycle counts of d_out_timing refer to. */
+int pam_sm_clock_khz(pam_handle* h, int32_t* khz);
+
 /* Same as pam_track_sequences with HOST buffers: allocates/reuses device workspace inside the
- * handle, copies in, runs, copies out, synchronises.  `fresh` != 0 restarts the trackers first. */
+ * handle, copies in, runs, copies out, synchronises.  `fresh` != 0 restarts the trackers first.
+ * Capacity warnings do not fail the call (query them with pam_track_host_status). */
 int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0, int32_t fresh,
                              const float* h_dets, const int32_t* h_counts, int32_t* h_out_count,
                              int32_t* h_out_ids, float* h_out_joints, uint8_t* h_out_nviews,
-                             int32_t* h_out_assoc);
+                             int32_t* h_out_assoc, int32_t* h_out_timing);
+
+/* pam_track_status for the internal state of the _host path. */
+int pam_track_host_status(pam_handle* h, int32_t S, int32_t* h_status);
 
 /* Copy the internal state of the _host path (S sequences) to a host buffer of S*seq_bytes. */
 int pam_track_state_to_host(pam_handle* h, int32_t S, void* h_state);

@@ -28,8 +28,8 @@ class PamStateLayout(C.Structure):
     _fields_ = [
         ("seq_bytes", C.c_int64), ("off_header", C.c_int64), ("off_meta", C.c_int64),
         ("off_hist", C.c_int64), ("off_view", C.c_int64), ("off_vel", C.c_int64),
-        ("off_nviews", C.c_int64), ("meta_ints", C.c_int32), ("hist_ring", C.c_int32),
-        ("max_views", C.c_int32), ("max_order", C.c_int32),
+        ("off_nviews", C.c_int64), ("off_margin", C.c_int64), ("meta_ints", C.c_int32), ("hist_ring", C.c_int32),
+        ("max_views", C.c_int32), ("max_order", C.c_int32), ("header_ints", C.c_int32), ("n_margins", C.c_int32),
     ]
 
 
@@ -66,9 +66,13 @@ _PROTOTYPES = [
     ("pam_set_cameras", C.c_int, [_P, _P, _P, _P, _P]),
     ("pam_get_state_layout", C.c_int, [_P, C.POINTER(PamStateLayout)]),
     ("pam_track_reset", C.c_int, [_P, _P, C.c_int32, _P]),
-    ("pam_track_sequences", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("pam_track_sequences", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("pam_track_status", C.c_int, [_P, _P, C.c_int32, _P, _P]),
-    ("pam_track_sequences_host", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    ("pam_track_margins", C.c_int, [_P, _P, C.c_int32, _P, _P]),
+    ("pam_track_launch_info", C.c_int, [_P, C.c_int32, _P]),
+    ("pam_sm_clock_khz", C.c_int, [_P, _P]),
+    ("pam_track_sequences_host", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("pam_track_host_status", C.c_int, [_P, C.c_int32, _P]),
     ("pam_track_state_to_host", C.c_int, [_P, C.c_int32, _P]),
     ("pam_launch_count", C.c_int64, [_P]),
     ("pam_project_points", C.c_int, [_P, _P, C.c_int32, _P, _P]),

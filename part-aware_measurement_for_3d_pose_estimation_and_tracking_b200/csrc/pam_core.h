@@ -45,11 +45,12 @@
 #endif
 
 #define PAM_MAX_V 8        // cameras per rig handled by the stateful tracker
-#define PAM_MAX_TRK 16     // track slots per sequence
+#define PAM_MAX_TRK 32     // track slots per sequence (run-time value: pam_config.max_tracks)
 #define PAM_MAX_D 16       // detections per camera per frame
 #define PAM_MAX_J 32       // joints
 #define PAM_RECENT 5       // newest history entries the smoothing / velocity step keeps in registers
-#define PAM_MAX_HYP 32     // person hypotheses during new-track initialisation
+#define PAM_MAX_HYP 64     // person hypotheses during new-track initialisation (run-time value: min(V * D, 64))
+#define PAM_LSAP_N 64      // largest assignment problem solved inside the tracker (tracks, hypotheses <= 64)
 #define PAM_HIST 12        // smoothed-pose history ring (max_age + 2 <= PAM_HIST)
 #define PAM_MAX_RADIUS 8   // Gaussian radius int(4 sigma + 0.5)
 #define PAM_MAX_AGEW 8     // stale-view window + 1

@@ -1,4 +1,4 @@
-// pam_host.h -- host-side helpers shared by the C ABI (pam_capi.cu) and the test-only host
+// pam_host.h -- host-side helpers shared by the C ABI (pam_lib.cu) and the test-only host
 // harness (tests/hostemu/hostemu.cpp): pam_config validation and the launch-constant DevCfg.
 #pragma once
 #include <string>
@@ -11,15 +11,17 @@ namespace pam {
 // rigs with up to 32 cameras are served by the stateless batched ops only.
 inline bool tracker_capable(const pam_config& p) { return p.num_cameras <= PAM_MAX_V; }
 
-inline int make_devcfg(const pam_config& p, DevCfg& c, std::string& err) {
+// nbuf / raw_in_arena: the working-set flavour (arena_layout); the global state layout does not depend on them
+inline int make_devcfg(const pam_config& p, DevCfg& c, std::string& err, int nbuf = 2, bool raw_in_arena = true) {
     auto bad = [&](const char* m) { err = m; return (int)PAM_E_INVALID; };
     if (p.num_cameras < 1 || p.num_cameras > 32) return bad("num_cameras outside 1..32");
     if (p.num_joints < 1 || p.num_joints > PAM_MAX_J) return bad("num_joints outside 1..32");
     if (p.max_detections < 1 || p.max_detections > PAM_MAX_D) return bad("max_detections outside 1..16");
-    if (p.max_tracks < 1 || p.max_tracks > PAM_MAX_TRK) return bad("max_tracks outside 1..16");
+    if (p.max_tracks < 1 || p.max_tracks > PAM_MAX_TRK) return bad("max_tracks outside 1..32");
     if (p.max_age < 0 || p.max_age + 2 > PAM_HIST) return bad("max_age + 2 exceeds the history ring (12)");
     if (p.stale_window < 0 || p.stale_window + 1 > PAM_MAX_AGEW) return bad("stale_window outside 0..7");
     if (!(p.sigma > 0.0) || !(p.arm_sigma > 0.0)) return bad("sigma / arm_sigma must be positive");
+    c = DevCfg();
     c.V = p.num_cameras; c.J = p.num_joints; c.D = p.max_detections; c.max_trk = p.max_tracks;
     c.max_hyp = p.num_cameras * p.max_detections < PAM_MAX_HYP ? p.num_cameras * p.max_detections : PAM_MAX_HYP;
     c.n_init = p.n_init; c.max_age = p.max_age; c.min_valid = p.min_valid_joints; c.stale_window = p.stale_window;
@@ -40,14 +42,15 @@ inline int make_devcfg(const pam_config& p, DevCfg& c, std::string& err) {
     c.fail_limit = (double)p.num_joints / 3.0;
     c.init_thr_f32 = (float)p.init_threshold;
     state_layout(c);
+    if (tracker_capable(p)) arena_layout(c, nbuf, raw_in_arena);
     return PAM_OK;
 }
 
 inline void fill_layout(const DevCfg& c, pam_state_layout& L) {
     L.seq_bytes = c.seq_bytes; L.off_header = c.off_hdr; L.off_meta = c.off_meta; L.off_hist = c.off_hist;
-    L.off_view = c.off_view; L.off_vel = c.off_vel; L.off_nviews = c.off_nv;
+    L.off_view = c.off_view; L.off_vel = c.off_vel; L.off_nviews = c.off_nv; L.off_margin = c.off_margin;
     L.meta_ints = (int32_t)(sizeof(TrkMeta) / 4); L.hist_ring = PAM_HIST; L.max_views = PAM_MAX_V;
-    L.max_order = PAM_MAX_TRK;
+    L.max_order = PAM_MAX_TRK; L.header_ints = 8; L.n_margins = MG_COUNT;
 }
 
 }  // namespace pam

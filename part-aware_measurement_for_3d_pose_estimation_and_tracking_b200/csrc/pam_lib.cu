@@ -18,54 +18,41 @@
 using namespace pam;
 
 // ----------------------------------------------------------------------------------------------
-// persistent per-sequence tracker kernel: one CTA owns one sequence for all T frames
+// persistent tracker kernel: one thread GROUP (G warps) owns one sequence for all T frames; Q groups
+// (sequences) share a CTA and the camera constants it keeps in shared memory
 // ----------------------------------------------------------------------------------------------
-template <int AFF_UNROLL>
-struct DeviceCtxT {
+template <int G, int AFF_UNROLL>
+struct GroupCtx {
     static constexpr int kAffinityUnroll = AFF_UNROLL;
-    __host__ __device__ __forceinline__ int tid() const {
-#ifdef __CUDA_ARCH__
-        return threadIdx.x;
-#else
-        return 0;
-#endif
+    int t;        // thread index inside the group
+    int bar;      // named barrier of the group (1..15), unused for one-warp groups
+    __device__ __forceinline__ int tid() const { return t; }
+    __device__ __forceinline__ int nthreads() const { return G * 32; }
+    __device__ __forceinline__ void sync() const {
+        if (G == 1) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(G * 32) : "memory");
     }
-    __host__ __device__ __forceinline__ int nthreads() const {
-#ifdef __CUDA_ARCH__
-        return blockDim.x;
-#else
-        return 1;
-#endif
-    }
-    __host__ __device__ __forceinline__ void sync() const {
-#ifdef __CUDA_ARCH__
-        __syncthreads();
-#endif
-    }
-    __host__ __device__ __forceinline__ void atomic_inc(int* p) const {
-#ifdef __CUDA_ARCH__
-        atomicAdd(p, 1);
-#else
-        *p += 1;
-#endif
-    }
+    __device__ __forceinline__ void atomic_inc(int* p) const { atomicAdd(p, 1); }
+    __device__ __forceinline__ long long clock() const { return clock64(); }
 };
 
-// Asynchronous global -> shared staging of one frame's detections, issued for frame t+1 while frame t is
-// being processed, so the frame-serial chain never waits on HBM.  When the frame is a whole number of
+// Asynchronous global -> shared staging of one frame's detections.  When the frame is a whole number of
 // 16-byte units (Shelf: 3360 B) ONE thread issues ONE bulk copy through the TMA engine
-// (cp.async.bulk, completion counted in bytes on an mbarrier -- UBLKCP in SASS); otherwise all threads
-// issue 4-byte LDGSTS copies.  The V per-camera counts always go through LDGSTS.
+// (cp.async.bulk, completion counted in bytes on an mbarrier -- UBLKCP in SASS); otherwise all threads of
+// the group issue 4-byte LDGSTS copies.  The V per-camera counts always go through LDGSTS.
+// Two buffers: frame t+1 is staged while frame t is processed.  One buffer (throughput launches, half the
+// shared memory): the copy of frame t+1 starts as soon as frame t no longer needs its detections (after the
+// part-aware filter), and the many other sequences of the SM cover its latency.
 __device__ __forceinline__ bool stage_is_bulk(const float* gsrc, int nfloats) {
     return (nfloats & 3) == 0 && ((uintptr_t)gsrc & 15) == 0;
 }
-__device__ __forceinline__ void stage_frame(float* sdst, int* scnt, const float* gsrc, const int* gcnt, int nfloats,
-                                            int V, unsigned long long* mbar, bool bulk) {
+__device__ __forceinline__ void stage_frame(int t, int nt, float* sdst, int* scnt, const float* gsrc, const int* gcnt,
+                                            int nfloats, int V, unsigned long long* mbar, bool bulk) {
     if (bulk) {
-        if (threadIdx.x == 0) {
+        if (t == 0) {
             const unsigned dst = (unsigned)__cvta_generic_to_shared(sdst), bar = (unsigned)__cvta_generic_to_shared(mbar);
             const unsigned bytes = (unsigned)nfloats * 4u;
-            // order the generic-proxy reads of this buffer (two frames ago) before the async-proxy write
+            // order the generic-proxy reads of this buffer before the async-proxy write
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -73,11 +60,11 @@ __device__ __forceinline__ void stage_frame(float* sdst, int* scnt, const float*
         }
     } else {
         const unsigned sbase = (unsigned)__cvta_generic_to_shared(sdst);
-        PAM_NOUNROLL for (int i = threadIdx.x; i < nfloats; i += blockDim.x)
+        PAM_NOUNROLL for (int i = t; i < nfloats; i += nt)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbase + i * 4), "l"(gsrc + i) : "memory");
     }
     const unsigned cbase = (unsigned)__cvta_generic_to_shared(scnt);
-    PAM_NOUNROLL for (int i = threadIdx.x; i < V; i += blockDim.x)
+    PAM_NOUNROLL for (int i = t; i < V; i += nt)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cbase + i * 4), "l"(gcnt + i) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -94,12 +81,6 @@ __device__ __forceinline__ void stage_wait(unsigned long long* mbar, unsigned pa
     }
 }
 
-// dynamic shared memory of k_track_sequences: [arena doubles][2 x frame floats][2 x V counts]
-static inline size_t frame_floats_padded(const DevCfg& c) { return ((size_t)c.V * c.D * c.J * 3 + 3) / 4 * 4; }
-static inline size_t track_smem_bytes(const DevCfg& c) {
-    return (size_t)((arena_doubles(c) + 1) / 2 * 2) * 8 + 2 * frame_floats_padded(c) * 4 + 2 * PAM_MAX_V * 4;
-}
-
 struct TrackIO {
     const float* dets;      // [S][T][V][D][J][3]
     const int* counts;      // [S][T][V]
@@ -108,45 +89,65 @@ struct TrackIO {
     float* out_joints;      // [S][T][MT][J][3]
     unsigned char* out_nv;  // [S][T][MT][J]
     int* out_assoc;         // [S][T][V][D]
+    int* out_timing;        // [S][T][4]
     int seq_frames;         // frames between consecutive sequences in every tensor above (>= T)
     int* out_status;        // [S] final status word of each sequence, or null
 };
 
-#define PAM_TRACK_THREADS_MAX 256
+// single-buffer staging: frame_step tells us when the staged detections are dead.  The hook only carries the
+// index of the next frame; everything else is recomputed from values the kernel keeps anyway.
+struct StageHook {
+    int next;               // frame (inside the launch) to stage, -1 = nothing to do
+    int t, nt;
+    float* dbuf; int* cbuf; const float* gd; const int* gc; int nfl, V; unsigned long long* mbar; bool bulk;
+    __device__ __forceinline__ void dets_released() const {
+        if (next >= 0) stage_frame(t, nt, dbuf, cbuf, gd + (int64_t)next * nfl, gc + next * V, nfl, V, mbar, bulk);
+    }
+};
 
-template <int MAXT, int MINB, int TEAM>
+// dynamic shared memory of k_track_sequences: [camera constants][Q x sequence arena]
+static inline size_t track_smem_bytes(const DevCfg& c, int Q) {
+    return (size_t)cam_bytes_of(c) + (size_t)Q * c.arena_bytes;
+}
+
+#define PAM_TRACK_THREADS_MAX 1024
+
+template <class K, int MAXT, int MINB, int G>
 __global__ void __launch_bounds__(MAXT, MINB)
-k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, int T, int frame0, const TrackIO io) {
-    extern __shared__ double arena[];
-    __shared__ SeqShared sh;
-    DeviceCtxT<(MAXT * MINB <= 512) ? 4 : 2> ctx;     // <= 512 resident threads per SM: 128 registers each
-    const int s = blockIdx.x;
-    SeqGlobal g;
-    g.bind(c, state + (int64_t)s * c.seq_bytes);
-    const int nfl = c.V * c.D * c.J * 3;
-    const int nfl_pad = (nfl + 3) / 4 * 4;
-    float* dbuf = (float*)(arena + (arena_doubles(c) + 1) / 2 * 2);   // 16-byte aligned for cp.async
-    int* cbuf = (int*)(dbuf + 2 * nfl_pad);
-    const float* gd = io.dets + (int64_t)s * io.seq_frames * nfl;
-    const int* gc = io.counts + (int64_t)s * io.seq_frames * c.V;
-    __shared__ __align__(8) unsigned long long mbar[2];       // one transaction barrier per detection buffer
-    const bool bulk = stage_is_bulk(gd, nfl);
-    if (threadIdx.x == 0) {
-        carve(c, sh, arena, g);
-        const unsigned b0 = (unsigned)__cvta_generic_to_shared(&mbar[0]), b1 = (unsigned)__cvta_generic_to_shared(&mbar[1]);
+k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, int S, int T, int frame0, const TrackIO io) {
+    extern __shared__ __align__(128) char smem[];
+    CamShared<K>* cam = (CamShared<K>*)smem;
+    constexpr int NT = G * 32;
+    constexpr int CAMB = (int)((sizeof(CamShared<K>) + 127) / 128 * 128);
+    const int grp = (MAXT == NT) ? 0 : (int)threadIdx.x / NT;
+    const int Q = (MAXT == NT) ? 1 : (int)blockDim.x / NT;
+    GroupCtx<G, (MAXT * MINB <= 512) ? 4 : 2> ctx{(int)threadIdx.x - grp * NT, 1 + grp};   // <= 512 resident threads per SM: 128 registers each
+    char* arena = smem + CAMB + grp * c.arena_bytes;
+    load_cameras(threadIdx.x, blockDim.x, c, cam, cc);
+    SeqShared<K>& sh = *(SeqShared<K>*)arena;
+    if (ctx.tid() == 0) {
+        const unsigned b0 = (unsigned)__cvta_generic_to_shared(&sh.mbar[0]), b1 = (unsigned)__cvta_generic_to_shared(&sh.mbar[1]);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b0) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (T > 0) stage_frame(dbuf, cbuf, gd, gc, nfl, c.V, &mbar[0], bulk);
-    load_cameras(ctx, c, sh, cc);
-    load_state(ctx, c, sh, g);
-    if (T > 0) stage_wait(&mbar[0], 0u, bulk);
-    __syncthreads();
-#if defined(PAM_PHASE_TIMING)
-    if (threadIdx.x == 0) { for (int k = 0; k < 24; ++k) sh.phase_cyc[k] = 0; sh.tlast = clock64(); }
-#endif
+    const int s = blockIdx.x * Q + grp;
+    if (s >= S) return;                 // whole groups leave; every later barrier is per group
+    Seq<K> sq;
+    sq.bind(c, arena, cam, state + (int64_t)s * c.seq_bytes);
+    const int nfl = c.V * c.D * c.J * 3;
+    const int nfl_pad = c.frame_floats;
+    const int nbuf = c.nbuf;
+    float* dbuf = (float*)(arena + c.a_dets);
+    int* cbuf = &sh.cnt[0][0];
+    const float* gd = io.dets + (int64_t)s * io.seq_frames * nfl;
+    const int* gc = io.counts + (int64_t)s * io.seq_frames * c.V;
+    const bool bulk = stage_is_bulk(gd, nfl);
+    if (T > 0) stage_frame(ctx.tid(), NT, dbuf, cbuf, gd, gc, nfl, c.V, &sh.mbar[0], bulk);
+    load_state(ctx, c, sq);
+    if (T > 0) stage_wait(&sh.mbar[0], 0u, bulk);
+    ctx.sync();
     FrameOut o;
     {
         const int64_t f0 = (int64_t)s * io.seq_frames;
@@ -155,49 +156,42 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
         o.joints = io.out_joints ? io.out_joints + f0 * c.max_trk * c.J * 3 : nullptr;
         o.nviews = io.out_nv ? io.out_nv + f0 * c.max_trk * c.J : nullptr;
         o.assoc = io.out_assoc ? io.out_assoc + f0 * c.V * c.D : nullptr;
+        o.timing = io.out_timing ? io.out_timing + f0 * 4 : nullptr;
     }
     const int st_ids = c.max_trk, st_joints = c.max_trk * c.J * 3, st_nv = c.max_trk * c.J, st_assoc = c.V * c.D;
+    StageHook hook{-1, ctx.tid(), NT, dbuf, cbuf, gd, gc, nfl, c.V, &sh.mbar[0], bulk};
     PAM_NOUNROLL for (int t = 0; t < T; ++t) {
-        const int cur = t & 1;
-        if (t + 1 < T)
-            stage_frame(dbuf + (cur ^ 1) * nfl_pad, cbuf + (cur ^ 1) * PAM_MAX_V, gd + (int64_t)(t + 1) * nfl,
-                        gc + (t + 1) * c.V, nfl, c.V, &mbar[cur ^ 1], bulk);
-        if (TEAM > 1) frame_step<WarpTeam<TEAM>>(ctx, c, sh, g, frame0 + t, dbuf + cur * nfl_pad, cbuf + cur * PAM_MAX_V, o, gd, frame0);
-        else frame_step<SoloTeam>(ctx, c, sh, g, frame0 + t, dbuf + cur * nfl_pad, cbuf + cur * PAM_MAX_V, o, gd, frame0);
+        const int cur = (nbuf == 2) ? (t & 1) : 0, nxt = (nbuf == 2) ? (cur ^ 1) : 0;
+        const bool more = t + 1 < T;
+        hook.next = (more && nbuf == 1) ? t + 1 : -1;
+        if (more && nbuf == 2)
+            stage_frame(ctx.tid(), NT, dbuf + nxt * nfl_pad, cbuf + nxt * PAM_MAX_V, gd + (int64_t)(t + 1) * nfl,
+                        gc + (t + 1) * c.V, nfl, c.V, &sh.mbar[nxt], bulk);
+        frame_step(ctx, c, sq, frame0 + t, dbuf + cur * nfl_pad, cbuf + cur * PAM_MAX_V, o, gd, frame0, hook);
         if (o.count) o.count += 1;
         if (o.ids) o.ids += st_ids;
         if (o.joints) o.joints += st_joints;
         if (o.nviews) o.nviews += st_nv;
         if (o.assoc) o.assoc += st_assoc;
-        // buffer (t+1)&1 is used for the ((t+1)>>1)-th time: that is the parity of its barrier phase
-        if (t + 1 < T) stage_wait(&mbar[cur ^ 1], (unsigned)(((t + 1) >> 1) & 1), bulk);
-        __syncthreads();
-        PAM_MARK(8);
+        if (o.timing) o.timing += 4;
+        // two buffers: buffer (t+1)&1 is used for the ((t+1)>>1)-th time; one buffer: for the (t+1)-th time --
+        // that is the parity of its barrier phase
+        if (more) stage_wait(&sh.mbar[nxt], (unsigned)((nbuf == 2 ? ((t + 1) >> 1) : (t + 1)) & 1), bulk);
+        ctx.sync();
     }
-    persist_views(ctx, c, sh, g, gd, frame0, T > 0 ? dbuf + ((T - 1) & 1) * nfl_pad : nullptr, T - 1);
-    store_state(ctx, c, sh, g);
-    if (io.out_status && threadIdx.x == 0) {
+    // the launch's last frame is still staged on chip when its buffer was not reused
+    persist_views(ctx, c, sq, gd, frame0, T > 0 ? dbuf + ((nbuf == 2) ? ((T - 1) & 1) : 0) * nfl_pad : nullptr, T - 1);
+    store_state(ctx, c, sq);
+    if (io.out_status) {
         // the status word may live in mapped host memory and be polled by the caller (small-job path):
-        // everything this CTA wrote for the host (ordered before this point by the frame barriers) must be
-        // visible system-wide first
-        __threadfence_system();
-        *(volatile int*)(io.out_status + s) = sh.hdr.status;
+        // everything this group wrote for the host must be visible system-wide first, and nobody may still be
+        // reading the caller's input buffer (persist_views) when the host sees completion
+        ctx.sync();
+        if (ctx.tid() == 0) {
+            __threadfence_system();
+            *(volatile int*)(io.out_status + s) = sh.hdr.status | (sh.hdr.warn << 8);
+        }
     }
-#if defined(PAM_PHASE_TIMING)
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        static const char* nm[9] = {"1 age+reproj", "2 affinity", "3 assign", "4 add_pose+believe", "5 filter+dlt",
-                                    "6 smooth+motion+out", "7 lifecycle+reap", "8 init", "9 stage wait"};
-        long long tot = 0;
-        for (int k = 0; k < 9; ++k) tot += sh.phase_cyc[k];
-        for (int k = 0; k < 9; ++k)
-            printf("phase %-22s %9.0f cyc/frame %5.1f%%\n", nm[k], (double)sh.phase_cyc[k] / T, 100.0 * sh.phase_cyc[k] / tot);
-        static const char* sub[7] = {"5a pair tests", "5b conflict resolution", "5c gram fold", "5d solve",
-                                     "6a prologue", "6b smoothing", "6c velocity"};
-        for (int k = 0; k < 7; ++k)   // thread 0's item; the remainder of phase 5 (stores, barrier wait) stays in its row above
-            printf("  sub %-22s %9.0f cyc/frame\n", sub[k], (double)sh.phase_cyc[10 + k] / T);
-        printf("total %.0f cyc/frame\n", (double)tot / T);
-    }
-#endif
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -219,20 +213,20 @@ struct DevBuf {
 
 struct pam_handle {
     pam_config cfg;
-    DevCfg dc;
+    DevCfg dc;               // latency flavour of the working set: two detection buffers, raw pose in the arena
+    DevCfg dc_tp;            // throughput flavour: one detection buffer, raw pose in the sequence's HBM scratch
     int device = 0;
     bool have_cameras = false;
-    int track_threads = 128;
-    bool threads_forced = false;
-    int track_minblocks = 0;   // 0 = choose per launch
     int num_sms = 148;
-    int track_team = 0;        // 0 = choose per launch
+    int smem_optin = 227 * 1024;
+    int clock_khz = 0;
+    // PAM_TRACK_SHAPE="<G>:<Q>:<regs>[:lean]" forces the launch shape (development / tests)
+    int force_g = 0, force_q = 0, force_regs = 0, force_lean = -1;
     DevBuf cam;              // packed camera constants
     CamConst cc{};
     // workspace of the *_host entry points
-    DevBuf ws_state, ws_dets, ws_counts, ws_count, ws_ids, ws_joints, ws_nv, ws_assoc;
+    DevBuf ws_state, ws_dets, ws_counts, ws_count, ws_ids, ws_joints, ws_nv, ws_assoc, ws_timing;
     int ws_S = 0;
-    bool smem_opt_in = false;
     cudaStream_t ws_stream = nullptr, ws_in = nullptr, ws_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_k;
     char* zc = nullptr;        // pinned, device-mapped staging of the small-job path
@@ -267,7 +261,7 @@ const char* pam_status_string(int s) {
         case PAM_E_INVALID: return "invalid argument or configuration";
         case PAM_E_CUDA: return "CUDA runtime error";
         case PAM_E_NOCAMERAS: return "pam_set_cameras has not been called";
-        case PAM_E_CAPACITY: return "a sequence exceeded a capacity limit (tracks / hypotheses / detections)";
+        case PAM_E_CAPACITY: return "a sequence exceeded a capacity limit (tracks / hypotheses / detections): the excess was dropped";
         case PAM_E_INTERNAL: return "internal error";
         default: return "unknown status";
     }
@@ -294,19 +288,24 @@ int pam_create(const pam_config* cfg, int device, pam_handle** out) {
     }
     e = cudaSetDevice(device);
     if (e != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaSetDevice"); }
-    const char* nt = getenv("PAM_TRACK_THREADS");
-    if (nt) {
-        int v = atoi(nt);
-        if (v >= 32 && v <= PAM_TRACK_THREADS_MAX) { h->track_threads = (v / 32) * 32; h->threads_forced = true; }
+    if (tracker_capable(*cfg)) {
+        rc = make_devcfg(*cfg, h->dc_tp, err, 1, false);
+        if (rc != PAM_OK) { delete h; return fail(nullptr, rc, err); }
     } else {
-        int want = cfg->max_tracks * cfg->num_joints;     // one thread per (track, joint)
-        h->track_threads = want <= 64 ? 64 : (want <= 128 ? 128 : (want <= 192 ? 192 : 256));
+        h->dc_tp = h->dc;
     }
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
-    const char* tm = getenv("PAM_TRACK_TEAM");
-    if (tm) { int v = atoi(tm); if (v == 1 || v == 2) h->track_team = v; }
-    const char* mb = getenv("PAM_TRACK_MINBLOCKS");
-    if (mb) { int v = atoi(mb); if (v == 4 || v == 6 || v == 8 || v == 10 || v == 12) h->track_minblocks = v; }
+    cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device);
+    const char* shp = getenv("PAM_TRACK_SHAPE");
+    if (shp) {
+        int g = 0, q = 0, r = 0, lean = -1;
+        const int got = sscanf(shp, "%d:%d:%d:%d", &g, &q, &r, &lean);
+        if (got >= 1) h->force_g = g;
+        if (got >= 2) h->force_q = q;
+        if (got >= 3) h->force_regs = r;
+        if (got >= 4) h->force_lean = lean;
+    }
     *out = h;
     return PAM_OK;
 }
@@ -316,7 +315,7 @@ int pam_destroy(pam_handle* h) {
     cudaSetDevice(h->device);
     h->cam.release();
     h->ws_state.release(); h->ws_dets.release(); h->ws_counts.release(); h->ws_count.release();
-    h->ws_ids.release(); h->ws_joints.release(); h->ws_nv.release(); h->ws_assoc.release();
+    h->ws_ids.release(); h->ws_joints.release(); h->ws_nv.release(); h->ws_assoc.release(); h->ws_timing.release();
     if (h->ws_stream) cudaStreamDestroy(h->ws_stream);
     if (h->ws_in) cudaStreamDestroy(h->ws_in);
     if (h->ws_out) cudaStreamDestroy(h->ws_out);
@@ -359,90 +358,223 @@ int pam_track_reset(pam_handle* h, void* d_state, int32_t S, void* stream) {
     return PAM_OK;
 }
 
-typedef void (*track_kernel_t)(const DevCfg, const CamConst, char*, int, int, const TrackIO);
+typedef void (*track_kernel_t)(const DevCfg, const CamConst, char*, int, int, int, const TrackIO);
 
-// register budget variants: <= 128 threads with 4 / 6 / 8 CTAs per SM, or up to 256 threads
-// Launch shape per call.  Few sequences: latency matters -- one CTA per sequence with the full register
-// budget.  Many sequences: the kernel is latency/barrier bound, so more, smaller CTAs per SM win
-// (measured on B200, Shelf shape, final kernel: 128 thr x 8/SM 57 M frames/s, 96 x 8 59 M, 64 x 12 59 M at 12 per SM).
-// Two lanes per (track, joint) (PAM_TRACK_TEAM=2) measured no faster than one, so 1 is the default.
-static track_kernel_t pick_track_kernel(const pam_handle* h, int S, int* threads) {
+// Launch shapes.  The kernel source is one; the variants differ in the register budget (__launch_bounds__) and
+// in the warps per sequence G.  Q (sequences per CTA) is a run-time value: blockDim = Q * G * 32 <= maxt.
+struct TrackVariant {
+    int caps, maxt, minb, g, regs;
+    track_kernel_t fn;
+};
+#define PAM_VARIANT(K, caps, maxt, minb, g, regs) {caps, maxt, minb, g, regs, k_track_sequences<K, maxt, minb, g>}
+static const TrackVariant k_variants[] = {
+    // ---- Campus / Shelf shaped working sets -------------------------------------------------------
+    // one warp per sequence: throughput launches, 16-32 sequences per SM
+    PAM_VARIANT(CapsSmall, CAPS_SMALL, 256, 4, 1, 64),
+    PAM_VARIANT(CapsSmall, CAPS_SMALL, 224, 4, 1, 72),
+    PAM_VARIANT(CapsSmall, CAPS_SMALL, 256, 3, 1, 80),
+    PAM_VARIANT(CapsSmall, CAPS_SMALL, 256, 2, 1, 128),
+    // two warps per sequence
+    PAM_VARIANT(CapsSmall, CAPS_SMALL, 256, 4, 2, 64),
+    PAM_VARIANT(CapsSmall, CAPS_SMALL, 128, 6, 2, 80),
+    PAM_VARIANT(CapsSmall, CAPS_SMALL, 128, 4, 2, 128),
+    // three warps per sequence (the round-1 shape: one sequence per CTA, 8 CTAs per SM)
+    PAM_VARIANT(CapsSmall, CAPS_SMALL, 96, 8, 3, 80),
+    PAM_VARIANT(CapsSmall, CAPS_SMALL, 192, 4, 3, 80),
+    // four / eight warps per sequence: few sequences, latency matters, full register budget
+    PAM_VARIANT(CapsSmall, CAPS_SMALL, 128, 8, 4, 64),
+    PAM_VARIANT(CapsSmall, CAPS_SMALL, 128, 4, 4, 128),
+    PAM_VARIANT(CapsSmall, CAPS_SMALL, 256, 2, 8, 128),
+#if !defined(PAM_DEV_SMALL_ONLY)
+    // ---- Panoptic shaped ---------------------------------------------------------------------------
+    PAM_VARIANT(CapsMid, CAPS_MID, 256, 3, 1, 80),
+    PAM_VARIANT(CapsMid, CAPS_MID, 256, 2, 1, 128),
+    PAM_VARIANT(CapsMid, CAPS_MID, 128, 6, 2, 80),
+    PAM_VARIANT(CapsMid, CAPS_MID, 128, 4, 4, 128),
+    PAM_VARIANT(CapsMid, CAPS_MID, 256, 2, 8, 128),
+    // ---- anything the tracker accepts (8 cameras x 16 detections x 32 joints x 32 tracks) ------------
+    PAM_VARIANT(CapsMax, CAPS_MAX, 256, 2, 1, 128),
+    PAM_VARIANT(CapsMax, CAPS_MAX, 128, 4, 2, 128),
+    PAM_VARIANT(CapsMax, CAPS_MAX, 128, 4, 4, 128),
+    PAM_VARIANT(CapsMax, CAPS_MAX, 256, 2, 8, 128),
+#endif
+};
+static const int k_num_variants = (int)(sizeof(k_variants) / sizeof(k_variants[0]));
+
+struct TrackLaunch {
+    const TrackVariant* v = nullptr;
+    const DevCfg* cfg = nullptr;
+    int q = 1, threads = 0, ctas_per_sm = 0;
+    size_t smem = 0;
+};
+
+// CTAs of this shape one SM can hold (shared memory, threads, register-bound minb)
+static int resident_ctas(const pam_handle* h, const TrackVariant& v, const DevCfg& c, int q) {
+    const size_t smem = track_smem_bytes(c, q) + 1024;           // + the per-CTA reservation of the driver
+    if (track_smem_bytes(c, q) > (size_t)h->smem_optin) return 0;
+    int by_smem = (int)((size_t)228 * 1024 / smem);
+    int by_threads = 2048 / (q * v.g * 32);
+    int n = by_smem < by_threads ? by_smem : by_threads;
+    if (n > v.minb) n = v.minb;
+    if (n > 32) n = 32;
+    return n;
+}
+
+// Launch shape per call.  Few sequences per SM: latency matters -- many warps per sequence, full register
+// budget, two detection buffers.  Many sequences per SM: one warp per sequence, as many sequences resident as
+// the shared memory allows (no block barriers, nobody waits for a neighbour's phase), one detection buffer.
+static TrackLaunch pick_track_launch_g(const pam_handle* h, int S, int g, bool lean) {
+    TrackLaunch L;
     const int per_sm = (S + h->num_sms - 1) / h->num_sms;
-    const int team = h->track_team ? h->track_team : 1;
-    int nt = h->track_threads;                       // PAM_TRACK_THREADS or the size-based default
-    int mb = h->track_minblocks;
-    if (!h->threads_forced && nt <= 128 && team == 1 && !mb && per_sm >= 10) nt = 64;
-    // 7-9 sequences per SM: three warps per CTA (the fourth one of a 128-thread CTA has nothing to do in any
-    // phase of the usual shapes) leave 80 registers per thread at 8 CTAs per SM: 59 M against 57 M frames/s
-    if (!h->threads_forced && nt == 128 && team == 1 && !mb && per_sm >= 7 && per_sm < 10) nt = 96;
-    if (!mb) mb = nt > 128 ? (per_sm > 2 ? 4 : 2) : (nt <= 64 && per_sm >= 10 ? 12 : (per_sm >= 7 ? 8 : (per_sm > 4 ? 6 : 4)));
-    *threads = nt;
-    if (nt > 128) {
-        if (team > 1) return k_track_sequences<256, 2, 2>;
-        return mb >= 4 ? k_track_sequences<256, 4, 1> : k_track_sequences<256, 2, 1>;
+    L.cfg = lean ? &h->dc_tp : &h->dc;
+    int best = -1, best_res = -1;
+    for (int k = 0; k < k_num_variants; ++k) {
+        const TrackVariant& v = k_variants[k];
+        if (v.caps != L.cfg->caps || v.g != g) continue;
+        if (h->force_regs && v.regs != h->force_regs) continue;
+        int q = v.maxt / (g * 32);
+        if (h->force_q) q = h->force_q;
+        if (q * g * 32 > v.maxt || (g > 1 && q > 15)) continue;
+        // not more groups per CTA than the batch can fill on every SM
+        while (q > 1 && !h->force_q && (S + q - 1) / q < h->num_sms) --q;
+        // ... nor than fit into shared memory
+        while (q > 1 && !h->force_q && resident_ctas(h, v, *L.cfg, q) <= 0) --q;
+        const int ctas = resident_ctas(h, v, *L.cfg, q);
+        if (ctas <= 0) continue;
+        int res = ctas * q;
+        if (res >= per_sm && !h->force_regs) {
+            // room for the whole batch: among those variants prefer the larger register budget
+            res = per_sm * 1000 + v.regs;
+        }
+        if (res > best_res) { best_res = res; best = k; L.q = q; L.ctas_per_sm = ctas; }
     }
-    if (team > 1) return mb >= 6 ? k_track_sequences<128, 6, 2> : k_track_sequences<128, 4, 2>;
-    if (nt == 96 && team == 1) return k_track_sequences<96, 8, 1>;     // three warps, 85 registers, 8 CTAs per SM
-    if (nt <= 64 && mb >= 10) return mb >= 12 ? k_track_sequences<64, 12, 1> : k_track_sequences<64, 10, 1>;
-    switch (mb) {
-        case 8: case 10: case 12: return k_track_sequences<128, 8, 1>;
-        case 6: return k_track_sequences<128, 6, 1>;
-        default: return k_track_sequences<128, 4, 1>;
+    if (best < 0) return L;
+    L.v = &k_variants[best];
+    L.threads = L.q * g * 32;
+    L.smem = track_smem_bytes(*L.cfg, L.q);
+    return L;
+}
+
+static TrackLaunch pick_track_launch(const pam_handle* h, int S) {
+    const int per_sm = (S + h->num_sms - 1) / h->num_sms;
+    if (h->force_g) return pick_track_launch_g(h, S, h->force_g, h->force_lean >= 0 ? h->force_lean != 0 : h->force_g == 1);
+    const int want = per_sm <= 2 ? 4 : (per_sm <= 9 ? 3 : (per_sm <= 15 ? 2 : 1));
+    // not every capacity class has every group size: take the nearest one that exists and fits
+    static const int order[4][5] = {{1, 2, 3, 4, 8}, {2, 1, 3, 4, 8}, {3, 2, 4, 1, 8}, {4, 8, 3, 2, 1}};
+    const int* ord = order[want == 1 ? 0 : (want == 2 ? 1 : (want == 3 ? 2 : 3))];
+    for (int k = 0; k < 5; ++k) {
+        const int g = ord[k];
+        const bool lean = h->force_lean >= 0 ? (h->force_lean != 0) : (g == 1);
+        TrackLaunch L = pick_track_launch_g(h, S, g, lean);
+        if (L.v) return L;
     }
+    return TrackLaunch();
 }
 
 static int launch_track(pam_handle* h, void* d_state, int32_t S, int32_t T, int32_t frame0, const TrackIO& io,
                         cudaStream_t stream) {
-    const size_t smem = track_smem_bytes(h->dc);
-    int threads = h->track_threads;
-    track_kernel_t kern = pick_track_kernel(h, S, &threads);
-    if (smem + sizeof(SeqShared) > 48 * 1024)
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<S, threads, smem, stream>>>(h->dc, h->cc, (char*)d_state, T, frame0, io);
+    const TrackLaunch L = pick_track_launch(h, S);
+    if (!L.v) return fail(h, PAM_E_INVALID, "no launch shape fits this configuration into shared memory (PAM_TRACK_SHAPE?)");
+    CK(cudaFuncSetAttribute(L.v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    const int grid = (S + L.q - 1) / L.q;
+    L.v->fn<<<grid, L.threads, L.smem, stream>>>(*L.cfg, h->cc, (char*)d_state, S, T, frame0, io);
     h->launches += 1;
     CK(cudaGetLastError());
     return PAM_OK;
 }
 
+int pam_track_launch_info(pam_handle* h, int32_t S, int32_t* out8) {
+    if (!h || !out8 || S <= 0) return fail(h, PAM_E_INVALID, "bad argument");
+    if (!tracker_capable(h->cfg)) return fail(h, PAM_E_INVALID, "the stateful tracker handles at most 8 cameras");
+    const TrackLaunch L = pick_track_launch(h, S);
+    if (!L.v) return fail(h, PAM_E_INVALID, "no launch shape fits this configuration into shared memory");
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, L.v->fn));
+    out8[0] = L.v->g; out8[1] = L.q; out8[2] = L.threads; out8[3] = L.ctas_per_sm; out8[4] = (int32_t)L.smem;
+    out8[5] = fa.numRegs; out8[6] = L.cfg->arena_bytes; out8[7] = L.cfg->nbuf;
+    return PAM_OK;
+}
+
+int pam_sm_clock_khz(pam_handle* h, int32_t* khz) {
+    if (!h || !khz) return PAM_E_INVALID;
+    *khz = h->clock_khz;
+    return PAM_OK;
+}
+
 int pam_track_sequences(pam_handle* h, void* d_state, int32_t S, int32_t T, int32_t frame0, const float* d_dets,
                         const int32_t* d_counts, int32_t* d_out_count, int32_t* d_out_ids, float* d_out_joints,
-                        uint8_t* d_out_nviews, int32_t* d_out_assoc, void* stream) {
+                        uint8_t* d_out_nviews, int32_t* d_out_assoc, int32_t* d_out_timing, void* stream) {
     if (!h || !d_state || !d_dets || !d_counts || S < 0 || T < 0) return fail(h, PAM_E_INVALID, "bad argument");
     if (!h->have_cameras) return fail(h, PAM_E_NOCAMERAS, "pam_set_cameras has not been called");
     if (!tracker_capable(h->cfg)) return fail(h, PAM_E_INVALID, "the stateful tracker handles at most 8 cameras");
     if (S == 0 || T == 0) return PAM_OK;
     CK(cudaSetDevice(h->device));
-    TrackIO io{d_dets, d_counts, d_out_count, d_out_ids, d_out_joints, d_out_nviews, d_out_assoc, T, nullptr};
+    TrackIO io{d_dets, d_counts, d_out_count, d_out_ids, d_out_joints, d_out_nviews, d_out_assoc, d_out_timing, T, nullptr};
     return launch_track(h, d_state, S, T, frame0, io, (cudaStream_t)stream);
 }
 
-int pam_track_status(pam_handle* h, const void* d_state, int32_t S, int32_t* h_status, void* stream) {
-    if (!h || !d_state || S < 0) return fail(h, PAM_E_INVALID, "bad argument");
-    CK(cudaSetDevice(h->device));
-    std::vector<int32_t> tmp((size_t)S);
-    const char* base = (const char*)d_state + h->dc.off_hdr + offsetof(SeqHeader, status);
-    CK(cudaMemcpy2DAsync(tmp.data(), 4, base, (size_t)h->dc.seq_bytes, 4, (size_t)S, cudaMemcpyDeviceToHost,
-                         (cudaStream_t)stream));
-    CK(cudaStreamSynchronize((cudaStream_t)stream));
-    int bad = 0, first = -1, code = 0;
+static int status_message(pam_handle* h, const int32_t* st, int S) {
+    int hard = 0, warned = 0, first = -1, code = 0;
     for (int s = 0; s < S; ++s) {
-        if (h_status) h_status[s] = tmp[s];
-        if (tmp[s] != 0) { if (!bad) { first = s; code = tmp[s]; } ++bad; }
+        if (st[s] & 0xff) { if (!hard) { first = s; code = st[s] & 0xff; } ++hard; }
+        else if (st[s]) { if (!hard && !warned) { first = s; code = st[s] >> 8; } ++warned; }
     }
-    if (bad) {
-        static const char* names[] = {"ok", "track slots exhausted (raise max_tracks)", "hypothesis table exhausted",
-                                      "more detections than max_detections", "pose history ring exhausted"};
-        char msg[256];
-        snprintf(msg, sizeof msg, "%d sequence(s) hit a capacity limit; first: sequence %d: %s", bad, first,
-                 (code >= 0 && code <= 4) ? names[code] : "unknown");
+    char msg[320];
+    if (hard) {
+        snprintf(msg, sizeof msg, "%d sequence(s) stopped with an internal error; first: sequence %d, code %d%s", hard, first,
+                 code, code == SEQ_ERR_HIST_OVERFLOW ? " (pose history ring exhausted)" : "");
+        return fail(h, PAM_E_INTERNAL, msg);
+    }
+    if (warned) {
+        snprintf(msg, sizeof msg,
+                 "%d sequence(s) hit a capacity limit (the excess was dropped for that frame, tracking went on); first: "
+                 "sequence %d:%s%s%s", warned, first,
+                 (code & WARN_TRACK_OVERFLOW) ? " track slots exhausted (raise max_tracks)" : "",
+                 (code & WARN_HYP_OVERFLOW) ? " hypothesis table exhausted" : "",
+                 (code & WARN_DET_OVERFLOW) ? " more detections than max_detections" : "");
         return fail(h, PAM_E_CAPACITY, msg);
     }
     return PAM_OK;
 }
 
+int pam_track_status(pam_handle* h, const void* d_state, int32_t S, int32_t* h_status, void* stream) {
+    if (!h || !d_state || S < 0) return fail(h, PAM_E_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    std::vector<int32_t> tmp((size_t)S), wrn((size_t)S);
+    const char* base = (const char*)d_state + h->dc.off_hdr;
+    CK(cudaMemcpy2DAsync(tmp.data(), 4, base + offsetof(SeqHeader, status), (size_t)h->dc.seq_bytes, 4, (size_t)S,
+                         cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaMemcpy2DAsync(wrn.data(), 4, base + offsetof(SeqHeader, warn), (size_t)h->dc.seq_bytes, 4, (size_t)S,
+                         cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int s = 0; s < S; ++s) {
+        tmp[s] = (tmp[s] & 0xff) | (wrn[s] << 8);
+        if (h_status) h_status[s] = tmp[s];
+    }
+    return status_message(h, tmp.data(), S);
+}
+
+int pam_track_host_status(pam_handle* h, int32_t S, int32_t* h_status) {
+    if (!h || S <= 0 || S > h->ws_S || !h->ws_stream) return fail(h, PAM_E_INVALID, "bad argument");
+    return pam_track_status(h, h->ws_state.p, S, h_status, h->ws_stream);
+}
+
+int pam_track_margins(pam_handle* h, const void* d_state, int32_t S, double* h_margins, void* stream) {
+    if (!h || !d_state || !h_margins || S < 0) return fail(h, PAM_E_INVALID, "bad argument");
+#if defined(PAM_MARGIN)
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy2DAsync(h_margins, 8 * MG_COUNT, (const char*)d_state + h->dc.off_margin, (size_t)h->dc.seq_bytes,
+                         8 * MG_COUNT, (size_t)S, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return PAM_OK;
+#else
+    return fail(h, PAM_E_INVALID, "this libpam.so was built without -DPAM_MARGIN (tools/build_margin.sh)");
+#endif
+}
+
 int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0, int32_t fresh, const float* h_dets,
                              const int32_t* h_counts, int32_t* h_out_count, int32_t* h_out_ids, float* h_out_joints,
-                             uint8_t* h_out_nviews, int32_t* h_out_assoc) {
+                             uint8_t* h_out_nviews, int32_t* h_out_assoc, int32_t* h_out_timing) {
     if (!h || !h_dets || !h_counts || !h_out_count || S <= 0 || T <= 0) return fail(h, PAM_E_INVALID, "bad argument");
     if (!h->have_cameras) return fail(h, PAM_E_NOCAMERAS, "pam_set_cameras has not been called");
     if (!tracker_capable(h->cfg)) return fail(h, PAM_E_INVALID, "the stateful tracker handles at most 8 cameras");
@@ -453,7 +585,7 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
     const size_t ST = (size_t)S * T;
     const size_t b_dets = ST * c.V * c.D * c.J * 3 * 4, b_counts = ST * c.V * 4, b_count = ST * 4;
     const size_t b_ids = ST * c.max_trk * 4, b_joints = ST * c.max_trk * c.J * 3 * 4, b_nv = ST * c.max_trk * c.J;
-    const size_t b_assoc = ST * c.V * c.D * 4;
+    const size_t b_assoc = ST * c.V * c.D * 4, b_timing = ST * 16;
     if (fresh || S != h->ws_S) {
         CK(h->ws_state.reserve((size_t)c.seq_bytes * S));
         CK(cudaMemsetAsync(h->ws_state.p, 0, (size_t)c.seq_bytes * S, st));
@@ -466,7 +598,8 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
         auto up = [](size_t x) { return (x + 255) / 256 * 256; };
         const size_t o_dets = 0, o_counts = o_dets + up(b_dets), o_count = o_counts + up(b_counts);
         const size_t o_ids = o_count + up(b_count), o_joints = o_ids + up(b_ids), o_nv = o_joints + up(b_joints);
-        const size_t o_assoc = o_nv + up(b_nv), o_status = o_assoc + up(b_assoc), total = o_status + up((size_t)S * 4);
+        const size_t o_assoc = o_nv + up(b_nv), o_timing = o_assoc + up(b_assoc), o_status = o_timing + up(b_timing);
+        const size_t total = o_status + up((size_t)S * 4);
         if (total <= 256 * 1024) {
             if (total > h->zc_cap) {
                 if (h->zc) cudaFreeHost(h->zc);
@@ -481,9 +614,9 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
             memcpy(z + o_counts, h_counts, b_counts);
             TrackIO io{(const float*)(dz + o_dets), (const int32_t*)(dz + o_counts), (int32_t*)(dz + o_count),
                        h_out_ids ? (int32_t*)(dz + o_ids) : nullptr, h_out_joints ? (float*)(dz + o_joints) : nullptr,
-                       h_out_nviews ? (uint8_t*)(dz + o_nv) : nullptr, h_out_assoc ? (int32_t*)(dz + o_assoc) : nullptr, T,
-                       (int*)(dz + o_status)};
-            // completion is detected by polling the status words the CTAs write last (a few us sooner
+                       h_out_nviews ? (uint8_t*)(dz + o_nv) : nullptr, h_out_assoc ? (int32_t*)(dz + o_assoc) : nullptr,
+                       h_out_timing ? (int32_t*)(dz + o_timing) : nullptr, T, (int*)(dz + o_status)};
+            // completion is detected by polling the status words the groups write last (a few us sooner
             // than a stream synchronisation wakes up); bounded, then the stream is synchronised anyway
             volatile int32_t* stv = (volatile int32_t*)(z + o_status);
             const int32_t pending = 0x7fffffff;
@@ -507,9 +640,10 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
             if (h_out_joints) memcpy(h_out_joints, z + o_joints, b_joints);
             if (h_out_nviews) memcpy(h_out_nviews, z + o_nv, b_nv);
             if (h_out_assoc) memcpy(h_out_assoc, z + o_assoc, b_assoc);
+            if (h_out_timing) memcpy(h_out_timing, z + o_timing, b_timing);
             const int32_t* stw = (const int32_t*)(z + o_status);
             for (int s = 0; s < S; ++s)
-                if (stw[s] != 0) return pam_track_status(h, h->ws_state.p, S, nullptr, st);   // formats the message
+                if (stw[s] & 0xff) return status_message(h, stw, S);     // hard errors only; warnings: pam_track_host_status
             return PAM_OK;
         }
     }
@@ -520,6 +654,7 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
     if (h_out_joints) CK(h->ws_joints.reserve(b_joints));
     if (h_out_nviews) CK(h->ws_nv.reserve(b_nv));
     if (h_out_assoc) CK(h->ws_assoc.reserve(b_assoc));
+    if (h_out_timing) CK(h->ws_timing.reserve(b_timing));
     // Pipeline over chunks of frames: the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap
     // the kernel of chunk k (three streams; tracker state stays in HBM between the chunk launches).
     if (!h->ws_in) CK(cudaStreamCreateWithFlags(&h->ws_in, cudaStreamNonBlocking));
@@ -550,7 +685,7 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
     CK(cudaStreamWaitEvent(h->ws_in, h->ev_k[nchunks], 0));
     const size_t f_dets = (size_t)c.V * c.D * c.J * 3 * 4, f_counts = (size_t)c.V * 4, f_count = 4;
     const size_t f_ids = (size_t)c.max_trk * 4, f_joints = (size_t)c.max_trk * c.J * 3 * 4, f_nv = (size_t)c.max_trk * c.J;
-    const size_t f_assoc = (size_t)c.V * c.D * 4;
+    const size_t f_assoc = (size_t)c.V * c.D * 4, f_timing = 16;
     auto chunk2d = [&](void* dst, const void* src, size_t fbytes, int t0, int n, cudaMemcpyKind kind, cudaStream_t sx) {
         return cudaMemcpy2DAsync((char*)dst + (size_t)t0 * fbytes, (size_t)T * fbytes, (const char*)src + (size_t)t0 * fbytes,
                                  (size_t)T * fbytes, (size_t)n * fbytes, (size_t)S, kind, sx);
@@ -566,7 +701,8 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
                    h_out_ids ? (int32_t*)h->ws_ids.p + (size_t)t0 * c.max_trk : nullptr,
                    h_out_joints ? (float*)h->ws_joints.p + (size_t)t0 * (f_joints / 4) : nullptr,
                    h_out_nviews ? (uint8_t*)h->ws_nv.p + (size_t)t0 * f_nv : nullptr,
-                   h_out_assoc ? (int32_t*)h->ws_assoc.p + (size_t)t0 * (f_assoc / 4) : nullptr, T, nullptr};
+                   h_out_assoc ? (int32_t*)h->ws_assoc.p + (size_t)t0 * (f_assoc / 4) : nullptr,
+                   h_out_timing ? (int32_t*)h->ws_timing.p + (size_t)t0 * 4 : nullptr, T, nullptr};
         int rc = launch_track(h, h->ws_state.p, S, n, frame0 + t0, io, st);
         if (rc != PAM_OK) return rc;
         CK(cudaEventRecord(h->ev_k[k], st));
@@ -576,10 +712,16 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
         if (h_out_joints) CK(chunk2d(h_out_joints, h->ws_joints.p, f_joints, t0, n, cudaMemcpyDeviceToHost, h->ws_out));
         if (h_out_nviews) CK(chunk2d(h_out_nviews, h->ws_nv.p, f_nv, t0, n, cudaMemcpyDeviceToHost, h->ws_out));
         if (h_out_assoc) CK(chunk2d(h_out_assoc, h->ws_assoc.p, f_assoc, t0, n, cudaMemcpyDeviceToHost, h->ws_out));
+        if (h_out_timing) CK(chunk2d(h_out_timing, h->ws_timing.p, f_timing, t0, n, cudaMemcpyDeviceToHost, h->ws_out));
     }
     CK(cudaStreamSynchronize(h->ws_out));
     drain.armed = false;
-    return pam_track_status(h, h->ws_state.p, S, nullptr, st);
+    {   // hard errors fail the call; capacity warnings are left to pam_track_host_status
+        std::vector<int32_t> stv((size_t)S);
+        int rc = pam_track_status(h, h->ws_state.p, S, stv.data(), st);
+        if (rc == PAM_E_CAPACITY) rc = PAM_OK;
+        return rc;
+    }
 }
 
 int pam_track_state_to_host(pam_handle* h, int32_t S, void* h_state) {

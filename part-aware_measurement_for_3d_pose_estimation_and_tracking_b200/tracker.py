@@ -16,10 +16,19 @@ from . import _capi, camera as _camera
 TENTATIVE, CONFIRMED, DELETED = 1, 2, 3
 
 
+PAM_E_CAPACITY = -4
+WARN_TRACKS, WARN_HYPOTHESES, WARN_DETECTIONS = 1, 2, 4
+
+
 class PamError(RuntimeError):
     def __init__(self, status, message):
         super().__init__(f"libpam status {status}: {message}")
         self.status = status
+
+
+class PamCapacityWarning(UserWarning):
+    """A sequence needed more track slots / hypotheses / detections than configured: the excess was
+    dropped for that frame and tracking went on (the reference has no such limits)."""
 
 
 def _check(lib, handle, rc):
@@ -86,7 +95,7 @@ class SequenceTracker:
         self.next_frame = 0
 
     # -- device-pointer path ------------------------------------------------------------------
-    def alloc_outputs(self, T: int, nviews: bool = True, assoc: bool = False):
+    def alloc_outputs(self, T: int, nviews: bool = True, assoc: bool = False, timing: bool = False):
         torch = self._torch()
         dev = f"cuda:{self.device}"
         c = self.cfg
@@ -95,9 +104,12 @@ class SequenceTracker:
                    joints=torch.empty((self.S, T, c.max_tracks, c.num_joints, 3), dtype=torch.float32, device=dev))
         out["nviews"] = torch.empty((self.S, T, c.max_tracks, c.num_joints), dtype=torch.uint8, device=dev) if nviews else None
         out["assoc"] = torch.empty((self.S, T, c.num_cameras, c.max_detections), dtype=torch.int32, device=dev) if assoc else None
+        if timing:
+            out["timing"] = torch.zeros((self.S, T, 4), dtype=torch.int32, device=dev)
         return out
 
-    def run(self, dets, counts, out: Optional[dict] = None, frame0: Optional[int] = None, nviews=True, assoc=False):
+    def run(self, dets, counts, out: Optional[dict] = None, frame0: Optional[int] = None, nviews=True, assoc=False,
+            timing=False):
         """``dets`` (S,T,V,D,J,3) float32 and ``counts`` (S,T,V) int32 CUDA tensors.  Asynchronous on
         torch's current stream; returns the dict of output tensors."""
         torch = self._torch()
@@ -109,29 +121,61 @@ class SequenceTracker:
         if self._state is None:
             self.restart()
         if out is None:
-            out = self.alloc_outputs(T, nviews, assoc)
+            out = self.alloc_outputs(T, nviews, assoc, timing)
         f0 = self.next_frame if frame0 is None else frame0
         st = torch.cuda.current_stream(self.device).cuda_stream
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         rc = self.lib.pam_track_sequences(self.handle, p(self._state), S, T, f0, p(dets), p(counts), p(out["count"]),
                                           p(out["ids"]), p(out["joints"]), p(out.get("nviews")), p(out.get("assoc")),
-                                          C.c_void_p(st))
+                                          p(out.get("timing")), C.c_void_p(st))
         _check(self.lib, self.handle, rc)
         self.next_frame = f0 + T
         return out
 
-    def check(self):
-        """Synchronise and raise if any sequence overflowed a capacity limit."""
-        torch = self._torch()
-        status = np.zeros(self.S, np.int32)
-        st = torch.cuda.current_stream(self.device).cuda_stream
-        rc = self.lib.pam_track_status(self.handle, C.c_void_p(self._state.data_ptr()), self.S, _np_ptr(status), C.c_void_p(st))
+    def check(self, strict: bool = True, host_path: bool = False):
+        """Synchronise and return the per-sequence status words (hard error code | PAM_WARN bits << 8).
+        A hard error always raises; a capacity warning (excess tracks / hypotheses / detections were dropped
+        for a frame, tracking went on) raises when ``strict`` and is a ``PamCapacityWarning`` otherwise."""
+        S = self._host_S if host_path else self.S
+        status = np.zeros(S, np.int32)
+        if host_path:
+            rc = self.lib.pam_track_host_status(self.handle, S, _np_ptr(status))
+        else:
+            torch = self._torch()
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.pam_track_status(self.handle, C.c_void_p(self._state.data_ptr()), S, _np_ptr(status), C.c_void_p(st))
+        if rc == PAM_E_CAPACITY and not strict:
+            import warnings
+            warnings.warn((self.lib.pam_last_error(self.handle) or b"").decode(), PamCapacityWarning, stacklevel=2)
+            return status
         _check(self.lib, self.handle, rc)
         return status
 
+    def margins(self):
+        """Decision margins per sequence (PAM_MARGIN builds of the library only): array (S, n_margins)."""
+        torch = self._torch()
+        out = np.zeros((self.S, self.layout.n_margins), np.float64)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _check(self.lib, self.handle, self.lib.pam_track_margins(self.handle, C.c_void_p(self._state.data_ptr()), self.S,
+                                                                 _np_ptr(out), C.c_void_p(st)))
+        return out
+
+    def launch_info(self, S: Optional[int] = None) -> dict:
+        """Launch shape the tracker uses for ``S`` sequences (defaults to this tracker's batch)."""
+        v = np.zeros(8, np.int32)
+        _check(self.lib, self.handle, self.lib.pam_track_launch_info(self.handle, int(self.S if S is None else S), _np_ptr(v)))
+        keys = ("warps_per_sequence", "sequences_per_cta", "threads_per_cta", "ctas_per_sm", "smem_per_cta",
+                "registers_per_thread", "arena_bytes_per_sequence", "detection_buffers")
+        return dict(zip(keys, (int(x) for x in v)))
+
+    def sm_clock_khz(self) -> int:
+        v = C.c_int32(0)
+        _check(self.lib, self.handle, self.lib.pam_sm_clock_khz(self.handle, C.byref(v)))
+        return int(v.value)
+
     # -- host-buffer path (what a reference-side caller would use) ------------------------------
     def run_host(self, dets: np.ndarray, counts: np.ndarray, frame0: Optional[int] = None, fresh: bool = False,
-                 nviews: bool = True, assoc: bool = False, out: Optional[dict] = None):
+                 nviews: bool = True, assoc: bool = False, out: Optional[dict] = None, timing: bool = False):
         """numpy in, numpy out through ``pam_track_sequences_host`` (H2D + kernel + D2H + sync)."""
         c = self.cfg
         dets = np.ascontiguousarray(dets, np.float32)
@@ -142,13 +186,14 @@ class SequenceTracker:
             out = dict(count=np.empty((S, T), np.int32), ids=np.empty((S, T, c.max_tracks), np.int32),
                        joints=np.empty((S, T, c.max_tracks, c.num_joints, 3), np.float32),
                        nviews=np.empty((S, T, c.max_tracks, c.num_joints), np.uint8) if nviews else None,
-                       assoc=np.empty((S, T, c.num_cameras, c.max_detections), np.int32) if assoc else None)
+                       assoc=np.empty((S, T, c.num_cameras, c.max_detections), np.int32) if assoc else None,
+                       timing=np.zeros((S, T, 4), np.int32) if timing else None)
         if fresh:
             self.next_frame = 0
         f0 = self.next_frame if frame0 is None else frame0
         rc = self.lib.pam_track_sequences_host(self.handle, S, T, f0, 1 if fresh else 0, _np_ptr(dets), _np_ptr(counts),
                                                _np_ptr(out["count"]), _np_ptr(out["ids"]), _np_ptr(out["joints"]),
-                                               _np_ptr(out.get("nviews")), _np_ptr(out.get("assoc")))
+                                               _np_ptr(out.get("nviews")), _np_ptr(out.get("assoc")), _np_ptr(out.get("timing")))
         _check(self.lib, self.handle, rc)
         self.next_frame = f0 + T
         self._host_S = S
@@ -175,9 +220,9 @@ def parse_state(blob: np.ndarray, S: int, L, cfg):
     seqs = []
     for s in range(S):
         base = blob[s * L.seq_bytes:(s + 1) * L.seq_bytes]
-        hdr = base[L.off_header:L.off_header + 4 * (5 + L.max_order)].view(np.int32)
-        ntracks, next_id, status = int(hdr[0]), int(hdr[1]), int(hdr[2])
-        order = hdr[5:5 + ntracks]
+        hdr = base[L.off_header:L.off_header + 4 * L.header_ints].view(np.int32)
+        ntracks, next_id, status, warn = int(hdr[0]), int(hdr[1]), int(hdr[2]), int(hdr[5])
+        order = base[L.off_header + 4 * L.header_ints:L.off_header + 4 * L.header_ints + ntracks].view(np.int8)
         meta = base[L.off_meta:L.off_meta + 4 * L.meta_ints * MT].view(np.int32).reshape(MT, L.meta_ints)
         hist = base[L.off_hist:L.off_hist + 8 * MT * H * J * 3].view(np.float64).reshape(MT, H, J, 3)
         view = base[L.off_view:L.off_view + 4 * MT * V * J * 3].view(np.float32).reshape(MT, V, J, 3)
@@ -196,5 +241,5 @@ def parse_state(blob: np.ndarray, S: int, L, cfg):
             tracks.append(dict(track_id=int(m[0]), hits=int(m[1]), age=int(m[2]), time_since_update=int(m[3]),
                                state=int(m[4]), already_update=bool(m[5]), poses2d=poses2d, poses3d=poses3d,
                                velocity_3d=vel[slot].copy(), joint_views=nv[slot].copy()))
-        seqs.append(dict(tracks=tracks, next_id=next_id, status=status))
+        seqs.append(dict(tracks=tracks, next_id=next_id, status=status, warn=warn, warn_frames=int(hdr[6])))
     return seqs

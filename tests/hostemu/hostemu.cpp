@@ -11,30 +11,21 @@
 
 using namespace pam;
 
-extern "C" int hostemu_track_sequences(const pam_config* cfg, const float* P, const float* RKinv, const double* pos,
-                                       const float* F, int S, int T, int frame0, const float* dets,
-                                       const int32_t* counts, int32_t* out_count, int32_t* out_ids,
-                                       float* out_joints, uint8_t* out_nviews, int32_t* out_assoc,
-                                       int32_t* status, void* state_io /* may be null; S*seq_bytes, zero = fresh */) {
-    DevCfg c;
-    std::string err;
-    int rc = make_devcfg(*cfg, c, err);
-    if (rc != PAM_OK) return rc;
-    std::vector<char> own;
-    char* state = (char*)state_io;
-    if (!state) { own.assign((size_t)c.seq_bytes * S, 0); state = own.data(); }
-    std::vector<double> arena((size_t)arena_doubles(c));
-    SeqShared* sh = new SeqShared();
+template <class K>
+static int run_sequences(const DevCfg& c, const CamConst& cc, char* state, int S, int T, int frame0, const float* dets,
+                         const int32_t* counts, int32_t* out_count, int32_t* out_ids, float* out_joints,
+                         uint8_t* out_nviews, int32_t* out_assoc, int32_t* status) {
+    std::vector<double> arena((size_t)c.arena_bytes / 8 + 16);
+    std::vector<CamShared<K>> cam(1);
     HostCtx ctx;
-    CamConst cc{P, RKinv, pos, F};
+    NoHook hook;
+    load_cameras(0, 1, c, cam.data(), cc);
     const int64_t fstride = (int64_t)c.V * c.D * c.J * 3;
     for (int s = 0; s < S; ++s) {
-        std::memset((void*)sh, 0, sizeof(SeqShared));
-        SeqGlobal g;
-        g.bind(c, state + (int64_t)s * c.seq_bytes);
-        carve(c, *sh, arena.data(), g);
-        load_cameras(ctx, c, *sh, cc);
-        load_state(ctx, c, *sh, g);
+        std::memset((void*)arena.data(), 0, arena.size() * 8);
+        Seq<K> sq;
+        sq.bind(c, (char*)arena.data(), cam.data(), state + (int64_t)s * c.seq_bytes);
+        load_state(ctx, c, sq);
         for (int t = 0; t < T; ++t) {
             const int64_t ft = (int64_t)s * T + t;
             FrameOut o;
@@ -43,14 +34,53 @@ extern "C" int hostemu_track_sequences(const pam_config* cfg, const float* P, co
             o.joints = out_joints ? out_joints + ft * c.max_trk * c.J * 3 : nullptr;
             o.nviews = out_nviews ? out_nviews + ft * c.max_trk * c.J : nullptr;
             o.assoc = out_assoc ? out_assoc + ft * c.V * c.D : nullptr;
-            frame_step<SoloTeam>(ctx, c, *sh, g, frame0 + t, dets + ft * fstride, counts + ft * c.V, o,
-                                 dets + (int64_t)s * T * fstride, frame0);
+            o.timing = nullptr;
+            frame_step(ctx, c, sq, frame0 + t, dets + ft * fstride, counts + ft * c.V, o,
+                       dets + (int64_t)s * T * fstride, frame0, hook);
         }
-        persist_views(ctx, c, *sh, g, dets + (int64_t)s * T * fstride, frame0, (const float*)nullptr, -1);
-        store_state(ctx, c, *sh, g);
-        if (status) status[s] = sh->hdr.status;
+        persist_views(ctx, c, sq, dets + (int64_t)s * T * fstride, frame0, (const float*)nullptr, -1);
+        store_state(ctx, c, sq);
+        if (status) status[s] = sq.sh->hdr.status | (sq.sh->hdr.warn << 8);
     }
-    delete sh;
+    return PAM_OK;
+}
+
+extern "C" int hostemu_track_sequences(const pam_config* cfg, const float* P, const float* RKinv, const double* pos,
+                                       const float* F, int S, int T, int frame0, const float* dets,
+                                       const int32_t* counts, int32_t* out_count, int32_t* out_ids,
+                                       float* out_joints, uint8_t* out_nviews, int32_t* out_assoc,
+                                       int32_t* status, void* state_io /* may be null; S*seq_bytes, zero = fresh */) {
+    DevCfg c;
+    std::string err;
+    // PAM_HOSTEMU_LEAN=1: the throughput flavour of the working set (one detection buffer, raw pose in the
+    // sequence's global scratch); default: the latency flavour.  PAM_HOSTEMU_CAPS=0/1/2 forces a capacity class
+    // at least that large (the same configuration must give the same result in every class that holds it).
+    const char* lean = getenv("PAM_HOSTEMU_LEAN");
+    const bool is_lean = lean && lean[0] == '1';
+    int rc = make_devcfg(*cfg, c, err, is_lean ? 1 : 2, !is_lean);
+    if (rc != PAM_OK) return rc;
+    if (!tracker_capable(*cfg)) return PAM_E_INVALID;
+    const char* fc = getenv("PAM_HOSTEMU_CAPS");
+    if (fc && atoi(fc) > c.caps) force_caps(c, atoi(fc));
+    std::vector<char> own;
+    char* state = (char*)state_io;
+    if (!state) { own.assign((size_t)c.seq_bytes * S, 0); state = own.data(); }
+    CamConst cc{P, RKinv, pos, F};
+    if (c.caps == CAPS_SMALL)
+        return run_sequences<CapsSmall>(c, cc, state, S, T, frame0, dets, counts, out_count, out_ids, out_joints, out_nviews, out_assoc, status);
+    if (c.caps == CAPS_MID)
+        return run_sequences<CapsMid>(c, cc, state, S, T, frame0, dets, counts, out_count, out_ids, out_joints, out_nviews, out_assoc, status);
+    return run_sequences<CapsMax>(c, cc, state, S, T, frame0, dets, counts, out_count, out_ids, out_joints, out_nviews, out_assoc, status);
+}
+
+// decision margins of the sequences in `state` (PAM_MARGIN builds of the harness)
+extern "C" int hostemu_margins(const pam_config* cfg, const void* state, int S, double* out) {
+    DevCfg c;
+    std::string err;
+    int rc = make_devcfg(*cfg, c, err);
+    if (rc != PAM_OK) return rc;
+    for (int s = 0; s < S; ++s)
+        std::memcpy(out + (size_t)s * MG_COUNT, (const char*)state + (int64_t)s * c.seq_bytes + c.off_margin, 8 * MG_COUNT);
     return PAM_OK;
 }
 

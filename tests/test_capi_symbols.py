@@ -33,7 +33,7 @@ def test_abi_version_and_status_strings_without_gpu():
     if not os.path.exists(_capi.LIB_PATH):
         pytest.skip("libpam.so not built")
     lib = _capi.load_library()
-    assert lib.pam_abi_version() == 1
+    assert lib.pam_abi_version() == 2
     assert b"capacity" in lib.pam_status_string(-4)
 
 
@@ -65,7 +65,7 @@ def test_library_is_sm100a_and_stages_frames_with_tma():
     elfs = subprocess.run([cuobjdump, "-lelf", _capi.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", elfs))
     assert archs == {"sm_100a"}, elfs
-    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_Z17k_track_sequencesILi128ELi4ELi1EEvN3pam6DevCfgENS0_8CamConstEPcii7TrackIO",
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_Z17k_track_sequencesILi128ELi4ELi4EEvN3pam6DevCfgENS0_8CamConstEPciii7TrackIO",
                            _capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "SYNCS" in sass
     assert "DFMA" in sass and "MUFU.RSQ64H" in sass        # FP64 path with the short MUFU-seeded reciprocal square root

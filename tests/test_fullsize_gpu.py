@@ -1,11 +1,11 @@
 """BASELINE.json full-size configurations through the C ABI.
 
-config 0 (Campus-shaped, 2000 frames) is compared frame by frame with the oracle over its whole
-length.  Configs 1 (Shelf-shaped, 3200 frames) and 2 (Panoptic-shaped, 10 000 frames) are too long
-for the python oracle at every frame, so they are checked on an oracle prefix plus size-independent
-properties: bit-identical results when the frames are fed in uneven chunks, when the run is
-repeated, and when a sequence is tracked alone instead of inside a batch; and tracking quality
-against the synthetic ground truth."""
+Configs 0 (Campus-shaped, 2000 frames), 1 (Shelf-shaped, 3200 frames) and 2 (Panoptic-shaped, 10 000 frames)
+are each compared frame by frame with the oracle over their WHOLE length (one sequence each; the oracles run
+in a process pool beside the GPU work).  Configs 1 and 2 are additionally checked through size-independent
+properties on a batch: bit-identical results when the frames are fed in uneven chunks, when the run is
+repeated, and when a sequence is tracked alone instead of inside a batch; and tracking quality against the
+synthetic ground truth."""
 import numpy as np
 import pytest
 
@@ -49,6 +49,43 @@ def test_config0_campus_2000_frames_full_oracle_parity():
     oo, oa, _ = util.run_oracle(st)
     worst = util.compare_with_oracle(out, 0, st, oo, oa)
     assert worst < 5e-4 and out["count"].sum() > 5000
+
+
+def _oracle_full(shape):
+    """Worker: the oracle over the full length of sequence 0 of a named shape."""
+    from tests import util as u
+    from pam_b200 import synth as sy
+    st = sy.make_stream(shape, 0)
+    oo, oa, _ = u.run_oracle(st)
+    return shape, oo, oa
+
+
+@pytest.fixture(scope="module")
+def full_length_oracles():
+    """Start the full-length oracles of the Shelf and Panoptic configurations in two worker processes right
+    away (Panoptic: 10 000 frames x 8 people, about a minute of one core); tests collect them when needed."""
+    import multiprocessing as mp
+    pool = mp.get_context("spawn").Pool(2)
+    pending = {sh: pool.apply_async(_oracle_full, (sh,)) for sh in ("panoptic", "shelf")}
+    yield pending
+    pool.terminate()
+
+
+@pytest.mark.parametrize("shape", ["shelf", "panoptic"])
+def test_full_length_oracle_parity(shape, full_length_oracles):
+    """BASELINE configs 1 and 2 at their stated length: every frame of one sequence against the oracle
+    (ids, reported sets, per-joint view counts, associations exact; joints within 0.5 mm / 1e-3)."""
+    sh = synth.SHAPES[shape]
+    st = synth.make_stream(shape, 0)
+    assert st.T == sh.T
+    trk = _tracker(shape, st.rig, 1, st.dets.shape[2])
+    out = trk.run_host(st.dets[None], st.counts[None], fresh=True, nviews=True, assoc=True)
+    assert trk.check(host_path=True).tolist() == [0]
+    _, oo, oa = full_length_oracles[shape].get(timeout=900)
+    assert len(oo) == sh.T
+    worst = util.compare_with_oracle(out, 0, st, oo, oa)
+    assert worst < 5e-4 and out["count"].sum() > sh.T * (sh.P - 1)
+    print(f"{shape}: {sh.T} frames, max joint deviation {worst:.3e} m")
 
 
 @pytest.mark.parametrize("shape,S,prefix", [("shelf", 12, 250), ("panoptic", 2, 120)])

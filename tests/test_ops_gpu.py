@@ -44,6 +44,58 @@ def test_dense_allpairs_affinity_and_triangulation_match_oracle():
         assert np.abs(got[p] - st.gt[0, p]).max() < 0.25      # and it is the right person (outlier joints included)
 
 
+def test_dense_full_size_sampled_pairs_and_all_triangulations():
+    """config 3 at its stated size: 31 cameras x 64 people x 19 joints, M = 1984 detections.  The O(M^2) python
+    oracle cannot fill the whole (M, M, J) tensor in test time, so 2000 random (i, j) pairs (plus same-camera and
+    diagonal entries) of the device result are compared with generic.epipolar_distance stored as float32 like the
+    reference (utils/matching.py:96-112), and ALL 64 x 19 triangulations from 31 views with the oracle's DLT."""
+    st = synth.make_stream("dense", 0, 1, miss_prob=0.0, outlier_prob=0.01)
+    cams, ocams = _rig("dense")
+    V, J, P = st.shape.V, st.shape.J, st.shape.P
+    poses = np.concatenate([st.dets[0, c, :st.counts[0, c]].astype(np.float64) for c in range(V)])
+    cam_idx = np.concatenate([np.full(st.counts[0, c], c) for c in range(V)])
+    M = len(poses)
+    assert M == V * P == 1984
+    o = ops.GeometryOps(cams, J, synth.tracker_params("dense"))
+    aff, D = o.epipolar_allpairs(cam_idx, poses)
+    assert aff.shape == (M, M) and D.shape == (M, M, J) and aff.dtype == np.float32
+    aff2, _ = o.epipolar_allpairs(cam_idx, poses, want_dist=False)
+    assert np.array_equal(aff, aff2)
+    rng = np.random.default_rng(7)
+    pairs = [(int(a), int(b)) for a, b in rng.integers(0, M, size=(2000, 2))]
+    pairs += [(k, k) for k in (0, 1, M - 1)] + [(0, 1), (P, P + 5), (M - 2, M - 1)]      # diagonal + same-camera pairs
+    worst = 0.0
+    for a, b in pairs:
+        if a == b:
+            assert aff[a, b] == 0.0 and not D[a, b].any()
+            continue
+        if cam_idx[a] == cam_idx[b]:
+            assert aff[a, b] == np.float32(25.0)          # the reference's initial value, never overwritten
+            continue
+        a, b = min(a, b), max(a, b)                         # the reference evaluates the pair as (i < j)
+        d = generic.epipolar_distance(ocams[cam_idx[a]], poses[a], ocams[cam_idx[b]], poses[b])
+        sym = [(x[0] + x[1]) / 2 for x in d]
+        ref = np.asarray(sym, dtype=np.float32)             # stored into a float32 array by the reference
+        assert np.allclose(D[a, b], ref, rtol=1e-6, atol=1e-4), (a, b)
+        assert np.array_equal(D[a, b], D[b, a])
+        assert np.isclose(aff[a, b], np.float32(np.mean(sym)), rtol=1e-6, atol=1e-4)
+        assert aff[a, b] == aff[b, a]
+        worst = max(worst, float(np.abs(D[a, b] - ref).max()))
+    # all 64 x 19 triangulations from 31 views, ground-truth grouping, random ages
+    pm = np.zeros((P, V, J, 3))
+    for c in range(V):
+        for d in range(st.counts[0, c]):
+            pm[st.person_of_det[0, c, d], c] = st.dets[0, c, d]
+    Ts = rng.choice([0, 0, 0, 1, 2], size=(P, V))
+    got = o.triangulate(np.tile(np.arange(V), (P, 1)), pm, np.exp(-5.0 * Ts))
+    dmax = 0.0
+    for p in range(P):
+        ref = generic.dlt_all_views(ocams, list(Ts[p]), pm[p], 5)
+        dmax = max(dmax, float(np.abs(got[p] - ref).max()))
+    assert dmax < 5e-4
+    print(f"dense M={M}: {len(pairs)} sampled pairs, max |dD| {worst:.2e} px; {P * J} triangulations, max |dX| {dmax:.2e} m")
+
+
 @pytest.mark.parametrize("shape", ["campus", "panoptic"])
 def test_per_track_ops_match_oracle(shape):
     st = synth.make_stream(shape, 5, 3, miss_prob=0.0, outlier_prob=0.1)

@@ -113,25 +113,46 @@ def test_capacity_overflow_is_reported():
 
 
 @pytest.mark.parametrize("env", [
-    {"PAM_TRACK_THREADS": "96"},                                   # 3 warps x 8 CTAs/SM (default at 7-9 sequences per SM)
-    {"PAM_TRACK_THREADS": "64", "PAM_TRACK_MINBLOCKS": "12"},      # 2 warps x 12 CTAs/SM (default at >= 10 per SM)
-    {"PAM_TRACK_THREADS": "128", "PAM_TRACK_MINBLOCKS": "8"},      # 4 warps x 8 CTAs/SM, 64 registers
-    {"PAM_TRACK_THREADS": "256"},
-    {"PAM_TRACK_THREADS": "256", "PAM_TRACK_TEAM": "2"},           # two lanes per (track, joint)
+    {"PAM_TRACK_SHAPE": "1:8:64"},      # one warp per sequence, 8 sequences per CTA, 64 registers (32 sequences per SM)
+    {"PAM_TRACK_SHAPE": "1:7:72"},      # 28 sequences per SM
+    {"PAM_TRACK_SHAPE": "1:8:80"},      # 24 sequences per SM
+    {"PAM_TRACK_SHAPE": "1:3:128"},     # one warp per sequence, full register budget, ragged last CTA
+    {"PAM_TRACK_SHAPE": "1:8:80:0"},    # one warp per sequence with the latency flavour of the working set
+    {"PAM_TRACK_SHAPE": "2:4:64"},      # two warps per sequence (named barriers), 4 sequences per CTA
+    {"PAM_TRACK_SHAPE": "2:2:80"},
+    {"PAM_TRACK_SHAPE": "2:2:128:1"},   # ... with one detection buffer and the raw pose in HBM scratch
+    {"PAM_TRACK_SHAPE": "3:1:80"},      # three warps, one sequence per CTA (round-1 shape)
+    {"PAM_TRACK_SHAPE": "3:2:80:1"},
+    {"PAM_TRACK_SHAPE": "4:1:64"},
+    {"PAM_TRACK_SHAPE": "4:1:128"},     # single-stream default
+    {"PAM_TRACK_SHAPE": "8:1:128"},
+    # Panoptic-sized working set (12 track slots): capacity class "mid"
+    {"PAM_TRACK_SHAPE": "1:8:80", "max_tracks": "12"},
+    {"PAM_TRACK_SHAPE": "2:2:80", "max_tracks": "12"},
+    {"PAM_TRACK_SHAPE": "8:1:128", "max_tracks": "12"},
+    # largest working set (32 track slots): capacity class "max"
+    {"PAM_TRACK_SHAPE": "1:2:128", "max_tracks": "32"},
+    {"PAM_TRACK_SHAPE": "4:1:128", "max_tracks": "32"},
 ])
 def test_every_launch_shape_matches_oracle(env, monkeypatch):
-    """The launch shape is picked from the batch size; small test batches only ever see the single-stream
-    shape, so every other register / CTA-size variant is forced here (read at pam_create) and checked."""
+    """The launch shape (warps per sequence : sequences per CTA : register budget [: lean working set]) is picked
+    from the batch size; small test batches only ever see the single-stream shape, so every other variant is
+    forced here (read at pam_create) and checked."""
     import torch
+    env = dict(env)
+    max_tracks = int(env.pop("max_tracks", "8"))
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    streams = [synth.make_stream("shelf", 40 + s, 150, miss_prob=0.08, outlier_prob=0.04, enter_stagger=10 * s) for s in range(3)]
-    trk = _tracker_for(streams)
+    streams = [synth.make_stream("shelf", 40 + s, 150, miss_prob=0.08, outlier_prob=0.04, enter_stagger=10 * s) for s in range(5)]
+    trk = _tracker_for(streams, max_tracks=max_tracks)
     dets = torch.from_numpy(np.stack([st.dets for st in streams])).cuda()
     counts = torch.from_numpy(np.stack([st.counts for st in streams])).cuda()
     out = trk.run(dets, counts, nviews=True, assoc=True)
-    assert trk.check().tolist() == [0, 0, 0]
-    out = {k: v.cpu().numpy() for k, v in out.items()}
+    assert trk.check().tolist() == [0] * 5
+    info = trk.launch_info()
+    g, q = (int(x) for x in env["PAM_TRACK_SHAPE"].split(":")[:2])
+    assert (info["warps_per_sequence"], info["sequences_per_cta"]) == (g, q), info
+    out = {k: v.cpu().numpy() for k, v in out.items() if v is not None}
     for s, st in enumerate(streams):
         oo, oa, _ = util.run_oracle(st)
         util.compare_with_oracle(out, s, st, oo, oa)
