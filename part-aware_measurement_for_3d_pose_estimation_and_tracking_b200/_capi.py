@@ -33,6 +33,11 @@ class PamStateLayout(C.Structure):
     ]
 
 
+class PamStreamViews(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("dets", "counts", "out_count", "out_ids", "out_joints", "out_nviews",
+                                          "out_assoc", "out_timing", "out_status")]
+
+
 def make_config(params, num_cameras, max_detections, max_tracks, arm_joints=(9, 10), min_valid_joints=10,
                 stale_window=3, veto_believe=0.5) -> PamConfig:
     """``params``: mapping / attribute object with the ``iter_args`` fields of
@@ -74,6 +79,10 @@ _PROTOTYPES = [
     ("pam_track_sequences_host", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("pam_track_host_status", C.c_int, [_P, C.c_int32, _P]),
     ("pam_track_state_to_host", C.c_int, [_P, C.c_int32, _P]),
+    ("pam_stream_open", C.c_int, [_P, C.c_int32]),
+    ("pam_stream_buffers", C.c_int, [_P, C.POINTER(PamStreamViews)]),
+    ("pam_stream_step", C.c_int, [_P, C.c_int32]),
+    ("pam_stream_close", C.c_int, [_P]),
     ("pam_launch_count", C.c_int64, [_P]),
     ("pam_project_points", C.c_int, [_P, _P, C.c_int32, _P, _P]),
     ("pam_assoc_affinity", C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),

@@ -32,6 +32,13 @@ struct GroupCtx {
         if (G == 1) __syncwarp();
         else asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(G * 32) : "memory");
     }
+    // the seven barriers every frame passes; convoy level 2 makes them span the sequences of the CTA, so that all
+    // its warps walk the frame's code together (instruction-cache locality at the price of waiting for the slowest)
+    int convoy_threads;
+    __device__ __forceinline__ void phase_sync() const {
+        if (convoy_threads) asm volatile("bar.sync 0, %0;" ::"r"(convoy_threads) : "memory");
+        else sync();
+    }
     __device__ __forceinline__ void atomic_inc(int* p) const { atomicAdd(p, 1); }
     __device__ __forceinline__ long long clock() const { return clock64(); }
 };
@@ -119,9 +126,11 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
     CamShared<K>* cam = (CamShared<K>*)smem;
     constexpr int NT = G * 32;
     constexpr int CAMB = (int)((sizeof(CamShared<K>) + 127) / 128 * 128);
-    const int grp = (MAXT == NT) ? 0 : (int)threadIdx.x / NT;
+    // warp-uniform by construction (a group is made of whole warps); saying so lets the compiler keep the
+    // group's base addresses in uniform registers instead of recomputing them from threadIdx all over the frame
+    const int grp = (MAXT == NT) ? 0 : __shfl_sync(0xffffffffu, (int)threadIdx.x / NT, 0);
     const int Q = (MAXT == NT) ? 1 : (int)blockDim.x / NT;
-    GroupCtx<G, (MAXT * MINB <= 512) ? 4 : 2> ctx{(int)threadIdx.x - grp * NT, 1 + grp};   // <= 512 resident threads per SM: 128 registers each
+    GroupCtx<G, (MAXT * MINB <= 512) ? 4 : 2> ctx{(int)threadIdx.x - grp * NT, 1 + grp, 0};   // <= 512 resident threads per SM: 128 registers each
     char* arena = smem + CAMB + grp * c.arena_bytes;
     load_cameras(threadIdx.x, blockDim.x, c, cam, cc);
     SeqShared<K>& sh = *(SeqShared<K>*)arena;
@@ -160,7 +169,12 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
     }
     const int st_ids = c.max_trk, st_joints = c.max_trk * c.J * 3, st_nv = c.max_trk * c.J, st_assoc = c.V * c.D;
     StageHook hook{-1, ctx.tid(), NT, dbuf, cbuf, gd, gc, nfl, c.V, &sh.mbar[0], bulk};
+    // convoy: the sequences of a CTA start every frame together, so their warps walk the same code at about the
+    // same time and share instruction fetches (24 independent warps otherwise thrash the instruction caches)
+    const int convoy_threads = (c.convoy && G == 1 && Q > 1) ? (((S - (int)blockIdx.x * Q) < Q ? (S - (int)blockIdx.x * Q) : Q) * NT) : 0;
+    if (c.convoy >= 2 && G == 1 && convoy_threads > NT) ctx.convoy_threads = convoy_threads;
     PAM_NOUNROLL for (int t = 0; t < T; ++t) {
+        if (convoy_threads > NT) asm volatile("bar.sync 0, %0;" ::"r"(convoy_threads) : "memory");
         const int cur = (nbuf == 2) ? (t & 1) : 0, nxt = (nbuf == 2) ? (cur ^ 1) : 0;
         const bool more = t + 1 < T;
         hook.next = (more && nbuf == 1) ? t + 1 : -1;
@@ -191,6 +205,100 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
             __threadfence_system();
             *(volatile int*)(io.out_status + s) = sh.hdr.status | (sh.hdr.warn << 8);
         }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// resident per-frame kernel ("stream mode"): the literal call pattern of the reference is ONE tracking() call
+// per frame (src/ivclabpose.py:257).  A launch per call costs launch + state load/store + completion latency, so
+// for that pattern one CTA stays resident: it polls a command word in pinned, device-mapped host memory, reads the
+// frame's detections from the same slot over PCIe, runs frame_step with the tracker state kept in shared memory, and
+// writes the results and a completion word back.  The host side of a call is: fill the slot, bump the command
+// word, spin on the completion word.
+// ----------------------------------------------------------------------------------------------
+enum { STREAM_CMD_IDLE = 0, STREAM_CMD_EXIT = -1 };
+struct StreamSlot {                      // offsets (bytes) into the mapped slot, computed by the host
+    int o_cmd, o_frame, o_counts, o_dets, o_done, o_count, o_ids, o_joints, o_nv, o_assoc, o_timing, o_status, bytes;
+};
+
+template <class K, int G>
+__global__ void __launch_bounds__(G * 32, 1)
+k_track_stream(const DevCfg c, const CamConst cc, char* __restrict__ state, char* __restrict__ slot, const StreamSlot so,
+               long long idle_limit_cycles) {
+    extern __shared__ __align__(128) char smem[];
+    CamShared<K>* cam = (CamShared<K>*)smem;
+    constexpr int NT = G * 32;
+    constexpr int CAMB = (int)((sizeof(CamShared<K>) + 127) / 128 * 128);
+    GroupCtx<G, 4> ctx{(int)threadIdx.x, 1, 0};
+    char* arena = smem + CAMB;
+    load_cameras(threadIdx.x, NT, c, cam, cc);
+    SeqShared<K>& sh = *(SeqShared<K>*)arena;
+    __shared__ int s_cmd, s_frame;
+    __syncthreads();
+    Seq<K> sq;
+    sq.bind(c, arena, cam, state);
+    load_state(ctx, c, sq);
+    const int nfl = c.V * c.D * c.J * 3;
+    float* dbuf = (float*)(arena + c.a_dets);
+    int* cbuf = &sh.cnt[0][0];
+    volatile int* h_cmd = (volatile int*)(slot + so.o_cmd);
+    const volatile float* h_dets = (const volatile float*)(slot + so.o_dets);
+    const volatile int* h_counts = (const volatile int*)(slot + so.o_counts);
+    FrameOut o;
+    o.count = (int*)(slot + so.o_count); o.ids = (int*)(slot + so.o_ids); o.joints = (float*)(slot + so.o_joints);
+    o.nviews = (unsigned char*)(slot + so.o_nv); o.assoc = (int*)(slot + so.o_assoc); o.timing = (int*)(slot + so.o_timing);
+    NoHook hook;
+    int last_seq = 0;
+    ctx.sync();
+    for (;;) {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            int cmd;
+            for (;;) {
+                cmd = *h_cmd;
+                if (cmd != last_seq) break;
+                if (clock64() - t0 > idle_limit_cycles) { cmd = STREAM_CMD_EXIT; break; }    // nobody is calling: free the SM
+            }
+            s_cmd = cmd;
+            if (cmd != STREAM_CMD_EXIT) s_frame = *(volatile int*)(slot + so.o_frame);
+        }
+        ctx.sync();
+        const int cmd = s_cmd;
+        if (cmd == STREAM_CMD_EXIT) break;
+        last_seq = cmd;
+        const int frame = s_frame;
+        // this frame's detections: host memory -> shared memory, all threads, 16 bytes per request when aligned
+        if ((nfl & 3) == 0) {
+            const volatile float4* src = (const volatile float4*)h_dets;
+            float4* dst = (float4*)dbuf;
+            PAM_NOUNROLL for (int i = threadIdx.x; i < nfl / 4; i += NT) {
+                float4 v;
+                v.x = src[i].x; v.y = src[i].y; v.z = src[i].z; v.w = src[i].w;
+                dst[i] = v;
+            }
+        } else {
+            PAM_NOUNROLL for (int i = threadIdx.x; i < nfl; i += NT) dbuf[i] = h_dets[i];
+        }
+        if (threadIdx.x < c.V) cbuf[threadIdx.x] = h_counts[threadIdx.x];
+        ctx.sync();
+        // stale views are read from the persisted copies (gin_frame0 = frame: only this frame's views count as
+        // "inside the launch"), which persist_views refreshes after every frame
+        frame_step(ctx, c, sq, frame, dbuf, cbuf, o, dbuf, frame, hook);
+        ctx.sync();
+        persist_views(ctx, c, sq, dbuf, frame, dbuf, 0);
+        __threadfence_system();
+        ctx.sync();
+        if (threadIdx.x == 0) {
+            *(volatile int*)(slot + so.o_status) = sh.hdr.status | (sh.hdr.warn << 8);
+            __threadfence_system();
+            *(volatile int*)(slot + so.o_done) = cmd;
+        }
+    }
+    store_state(ctx, c, sq);
+    ctx.sync();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        *(volatile int*)(slot + so.o_done) = STREAM_CMD_EXIT;
     }
 }
 
@@ -229,6 +337,13 @@ struct pam_handle {
     int ws_S = 0;
     cudaStream_t ws_stream = nullptr, ws_in = nullptr, ws_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_k;
+    // stream mode (resident per-frame kernel)
+    char* st_slot = nullptr;   // pinned, device-mapped command / result slot
+    char* st_slot_dev = nullptr;
+    StreamSlot st_so{};
+    bool st_running = false;
+    int st_seq = 0;
+    cudaStream_t st_stream = nullptr;
     char* zc = nullptr;        // pinned, device-mapped staging of the small-job path
     size_t zc_cap = 0;
     int64_t launches = 0;
@@ -297,6 +412,13 @@ int pam_create(const pam_config* cfg, int device, pam_handle** out) {
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device);
+    {
+        // default 1: the one-warp sequences of a CTA start every frame together (+10 % on B200: the 16-24
+        // independent warps of an SM otherwise thrash the instruction caches); 2: every phase together; 0: free running
+        const char* cv = getenv("PAM_TRACK_CONVOY");
+        const int convoy = cv ? atoi(cv) : 1;
+        h->dc.convoy = convoy; h->dc_tp.convoy = convoy;
+    }
     const char* shp = getenv("PAM_TRACK_SHAPE");
     if (shp) {
         int g = 0, q = 0, r = 0, lean = -1;
@@ -313,6 +435,9 @@ int pam_create(const pam_config* cfg, int device, pam_handle** out) {
 int pam_destroy(pam_handle* h) {
     if (!h) return PAM_OK;
     cudaSetDevice(h->device);
+    pam_stream_close(h);
+    if (h->st_slot) cudaFreeHost(h->st_slot);
+    if (h->st_stream) cudaStreamDestroy(h->st_stream);
     h->cam.release();
     h->ws_state.release(); h->ws_dets.release(); h->ws_counts.release(); h->ws_count.release();
     h->ws_ids.release(); h->ws_joints.release(); h->ws_nv.release(); h->ws_assoc.release(); h->ws_timing.release();
@@ -369,32 +494,26 @@ struct TrackVariant {
 #define PAM_VARIANT(K, caps, maxt, minb, g, regs) {caps, maxt, minb, g, regs, k_track_sequences<K, maxt, minb, g>}
 static const TrackVariant k_variants[] = {
     // ---- Campus / Shelf shaped working sets -------------------------------------------------------
-    // one warp per sequence: throughput launches, 16-32 sequences per SM
-    PAM_VARIANT(CapsSmall, CAPS_SMALL, 256, 4, 1, 64),
-    PAM_VARIANT(CapsSmall, CAPS_SMALL, 224, 4, 1, 72),
-    PAM_VARIANT(CapsSmall, CAPS_SMALL, 256, 3, 1, 80),
+    // one warp per sequence: throughput launches, 16-24 sequences per SM (measured on B200, Shelf shape,
+    // frames of a CTA started together: 67.7 M frames/s at 16 per SM with 128 registers, 68.9 M at 24 per SM
+    // with 80; without the convoy barrier 61.5 M; three warps per sequence at 8 per SM: 59 M)
     PAM_VARIANT(CapsSmall, CAPS_SMALL, 256, 2, 1, 128),
-    // two warps per sequence
-    PAM_VARIANT(CapsSmall, CAPS_SMALL, 256, 4, 2, 64),
-    PAM_VARIANT(CapsSmall, CAPS_SMALL, 128, 6, 2, 80),
-    PAM_VARIANT(CapsSmall, CAPS_SMALL, 128, 4, 2, 128),
-    // three warps per sequence (the round-1 shape: one sequence per CTA, 8 CTAs per SM)
+    PAM_VARIANT(CapsSmall, CAPS_SMALL, 384, 2, 1, 80),
+    PAM_VARIANT(CapsSmall, CAPS_SMALL, 256, 3, 1, 80),
+    // three warps per sequence, one sequence per CTA, 8 CTAs per SM: 5-11 sequences per SM
     PAM_VARIANT(CapsSmall, CAPS_SMALL, 96, 8, 3, 80),
-    PAM_VARIANT(CapsSmall, CAPS_SMALL, 192, 4, 3, 80),
     // four / eight warps per sequence: few sequences, latency matters, full register budget
-    PAM_VARIANT(CapsSmall, CAPS_SMALL, 128, 8, 4, 64),
     PAM_VARIANT(CapsSmall, CAPS_SMALL, 128, 4, 4, 128),
     PAM_VARIANT(CapsSmall, CAPS_SMALL, 256, 2, 8, 128),
 #if !defined(PAM_DEV_SMALL_ONLY)
     // ---- Panoptic shaped ---------------------------------------------------------------------------
+    PAM_VARIANT(CapsMid, CAPS_MID, 192, 2, 1, 128),
     PAM_VARIANT(CapsMid, CAPS_MID, 256, 3, 1, 80),
-    PAM_VARIANT(CapsMid, CAPS_MID, 256, 2, 1, 128),
-    PAM_VARIANT(CapsMid, CAPS_MID, 128, 6, 2, 80),
+    PAM_VARIANT(CapsMid, CAPS_MID, 96, 8, 3, 80),
     PAM_VARIANT(CapsMid, CAPS_MID, 128, 4, 4, 128),
     PAM_VARIANT(CapsMid, CAPS_MID, 256, 2, 8, 128),
     // ---- anything the tracker accepts (8 cameras x 16 detections x 32 joints x 32 tracks) ------------
     PAM_VARIANT(CapsMax, CAPS_MAX, 256, 2, 1, 128),
-    PAM_VARIANT(CapsMax, CAPS_MAX, 128, 4, 2, 128),
     PAM_VARIANT(CapsMax, CAPS_MAX, 128, 4, 4, 128),
     PAM_VARIANT(CapsMax, CAPS_MAX, 256, 2, 8, 128),
 #endif
@@ -458,7 +577,9 @@ static TrackLaunch pick_track_launch_g(const pam_handle* h, int S, int g, bool l
 static TrackLaunch pick_track_launch(const pam_handle* h, int S) {
     const int per_sm = (S + h->num_sms - 1) / h->num_sms;
     if (h->force_g) return pick_track_launch_g(h, S, h->force_g, h->force_lean >= 0 ? h->force_lean != 0 : h->force_g == 1);
-    const int want = per_sm <= 2 ? 4 : (per_sm <= 9 ? 3 : (per_sm <= 15 ? 2 : 1));
+    // measured (B200, Shelf shape): <= 4 sequences per SM four warps each (44.7 M frames/s at 4 per SM against 42.0 M
+    // with three), 5-11 three warps each, from 12 per SM one warp each
+    const int want = per_sm <= 4 ? 4 : (per_sm <= 11 ? 3 : 1);
     // not every capacity class has every group size: take the nearest one that exists and fits
     static const int order[4][5] = {{1, 2, 3, 4, 8}, {2, 1, 3, 4, 8}, {3, 2, 4, 1, 8}, {4, 8, 3, 2, 1}};
     const int* ord = order[want == 1 ? 0 : (want == 2 ? 1 : (want == 3 ? 2 : 3))];
@@ -579,6 +700,7 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
     if (!h->have_cameras) return fail(h, PAM_E_NOCAMERAS, "pam_set_cameras has not been called");
     if (!tracker_capable(h->cfg)) return fail(h, PAM_E_INVALID, "the stateful tracker handles at most 8 cameras");
     CK(cudaSetDevice(h->device));
+    if (h->st_running) { int rc = pam_stream_close(h); if (rc != PAM_OK) return rc; }
     if (!h->ws_stream) CK(cudaStreamCreateWithFlags(&h->ws_stream, cudaStreamNonBlocking));
     cudaStream_t st = h->ws_stream;
     const DevCfg& c = h->dc;
@@ -727,8 +849,123 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
 int pam_track_state_to_host(pam_handle* h, int32_t S, void* h_state) {
     if (!h || !h_state || S <= 0 || S > h->ws_S) return fail(h, PAM_E_INVALID, "bad argument");
     CK(cudaSetDevice(h->device));
+    if (h->st_running) { int rc = pam_stream_close(h); if (rc != PAM_OK) return rc; }   // state lives on chip while it runs
     CK(cudaMemcpyAsync(h_state, h->ws_state.p, (size_t)h->dc.seq_bytes * S, cudaMemcpyDeviceToHost, h->ws_stream));
     CK(cudaStreamSynchronize(h->ws_stream));
+    return PAM_OK;
+}
+
+// ---- stream mode ---------------------------------------------------------------------------------------
+typedef void (*stream_kernel_t)(const DevCfg, const CamConst, char*, char*, const StreamSlot, long long);
+
+static int stream_launch(pam_handle* h) {
+    const DevCfg& c = h->dc;
+    stream_kernel_t fn = c.caps == CAPS_SMALL ? k_track_stream<CapsSmall, 4>
+                       : (c.caps == CAPS_MID ? k_track_stream<CapsMid, 4> : k_track_stream<CapsMax, 8>);
+    const size_t smem = track_smem_bytes(c, 1);
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    *(volatile int*)(h->st_slot + h->st_so.o_done) = 0;
+    *(volatile int*)(h->st_slot + h->st_so.o_cmd) = 0;
+    h->st_seq = 0;
+    const long long idle = (long long)h->clock_khz * 1000;        // about one second of SM cycles
+    fn<<<1, c.caps == CAPS_MAX ? 256 : 128, smem, h->st_stream>>>(c, h->cc, (char*)h->ws_state.p, h->st_slot_dev, h->st_so, idle);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    h->st_running = true;
+    return PAM_OK;
+}
+
+int pam_stream_open(pam_handle* h, int32_t fresh) {
+    if (!h) return fail(h, PAM_E_INVALID, "null handle");
+    if (!h->have_cameras) return fail(h, PAM_E_NOCAMERAS, "pam_set_cameras has not been called");
+    if (!tracker_capable(h->cfg)) return fail(h, PAM_E_INVALID, "the stateful tracker handles at most 8 cameras");
+    CK(cudaSetDevice(h->device));
+    if (h->st_running) { int rc = pam_stream_close(h); if (rc != PAM_OK) return rc; }
+    if (!h->ws_stream) CK(cudaStreamCreateWithFlags(&h->ws_stream, cudaStreamNonBlocking));
+    if (!h->st_stream) CK(cudaStreamCreateWithFlags(&h->st_stream, cudaStreamNonBlocking));
+    const DevCfg& c = h->dc;
+    if (fresh || h->ws_S != 1) {
+        CK(h->ws_state.reserve((size_t)c.seq_bytes));
+        CK(cudaMemsetAsync(h->ws_state.p, 0, (size_t)c.seq_bytes, h->ws_stream));
+        CK(cudaStreamSynchronize(h->ws_stream));
+        h->ws_S = 1;
+    }
+    if (!h->st_slot) {
+        StreamSlot so;
+        int o = 0;
+        auto take = [&](size_t bytes) { const int at = o; o += (int)((bytes + 127) / 128 * 128); return at; };
+        so.o_cmd = take(4); so.o_frame = take(4); so.o_counts = take(4 * PAM_MAX_V);
+        so.o_dets = take((size_t)c.V * c.D * c.J * 3 * 4);
+        so.o_done = take(4); so.o_count = take(4); so.o_ids = take((size_t)c.max_trk * 4);
+        so.o_joints = take((size_t)c.max_trk * c.J * 3 * 4); so.o_nv = take((size_t)c.max_trk * c.J);
+        so.o_assoc = take((size_t)c.V * c.D * 4); so.o_timing = take(16); so.o_status = take(4);
+        so.bytes = o;
+        CK(cudaHostAlloc((void**)&h->st_slot, (size_t)o, cudaHostAllocMapped));
+        memset(h->st_slot, 0, (size_t)o);
+        CK(cudaHostGetDevicePointer((void**)&h->st_slot_dev, h->st_slot, 0));
+        h->st_so = so;
+    }
+    return stream_launch(h);
+}
+
+int pam_stream_buffers(pam_handle* h, pam_stream_views* v) {
+    if (!h || !v || !h->st_slot) return fail(h, PAM_E_INVALID, "stream not open");
+    const StreamSlot& so = h->st_so;
+    v->dets = (float*)(h->st_slot + so.o_dets); v->counts = (int32_t*)(h->st_slot + so.o_counts);
+    v->out_count = (int32_t*)(h->st_slot + so.o_count); v->out_ids = (int32_t*)(h->st_slot + so.o_ids);
+    v->out_joints = (float*)(h->st_slot + so.o_joints); v->out_nviews = (uint8_t*)(h->st_slot + so.o_nv);
+    v->out_assoc = (int32_t*)(h->st_slot + so.o_assoc); v->out_timing = (int32_t*)(h->st_slot + so.o_timing);
+    v->out_status = (int32_t*)(h->st_slot + so.o_status);
+    return PAM_OK;
+}
+
+int pam_stream_step(pam_handle* h, int32_t frame_id) {
+    if (!h || !h->st_slot) return fail(h, PAM_E_INVALID, "stream not open");
+    volatile int* cmd = (volatile int*)(h->st_slot + h->st_so.o_cmd);
+    volatile int* done = (volatile int*)(h->st_slot + h->st_so.o_done);
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if (!h->st_running || *done == STREAM_CMD_EXIT) {        // the kernel left after an idle second: start it again
+            CK(cudaSetDevice(h->device));
+            CK(cudaStreamSynchronize(h->st_stream));
+            h->st_running = false;
+            int rc = stream_launch(h);
+            if (rc != PAM_OK) return rc;
+        }
+        *(volatile int*)(h->st_slot + h->st_so.o_frame) = frame_id;
+        int seq = h->st_seq + 1;
+        if (seq <= 0) seq = 1;
+        h->st_seq = seq;
+        std::atomic_thread_fence(std::memory_order_release);     // inputs before the command word
+        *cmd = seq;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int spin = 0;; ++spin) {
+            const int d = *done;
+            if (d == seq) {
+                std::atomic_thread_fence(std::memory_order_acquire);
+                const int st = *(volatile int*)(h->st_slot + h->st_so.o_status);
+                if (st & 0xff) return status_message(h, &st, 1);
+                return PAM_OK;
+            }
+            if (d == STREAM_CMD_EXIT) break;                     // raced with the idle exit: relaunch and resubmit
+            if ((spin & 1023) == 1023) {
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) {
+                    cudaError_t e = cudaStreamQuery(h->st_stream);
+                    if (e != cudaErrorNotReady) { h->st_running = false; return cuda_fail(h, e == cudaSuccess ? cudaErrorUnknown : e, "resident kernel stopped"); }
+                    return fail(h, PAM_E_INTERNAL, "resident kernel did not answer within 5 s");
+                }
+            }
+        }
+    }
+    return fail(h, PAM_E_INTERNAL, "resident kernel keeps exiting");
+}
+
+int pam_stream_close(pam_handle* h) {
+    if (!h) return PAM_OK;
+    if (!h->st_running) return PAM_OK;
+    CK(cudaSetDevice(h->device));
+    *(volatile int*)(h->st_slot + h->st_so.o_cmd) = STREAM_CMD_EXIT;
+    CK(cudaStreamSynchronize(h->st_stream));       // the kernel stores the tracker state before it leaves
+    h->st_running = false;
     return PAM_OK;
 }
 

@@ -2,7 +2,8 @@
 //
 // frame_step<Ctx>() is executed by all threads of one thread GROUP (Ctx: 1..8 warps of a CTA; several
 // groups = several sequences share a CTA and its camera constants) which owns one sequence; phases are
-// separated by ctx.sync() (a warp barrier for one-warp groups, a named barrier otherwise).  Work inside
+// separated by ctx.phase_sync() / ctx.sync() (a warp barrier for one-warp groups, a named barrier otherwise;
+// phase_sync may span the CTA's sequences, see `convoy`).  Work inside
 // a phase is a group-stride loop over independent items (camera x track x detection, track x joint,
 // hypothesis x detection ...), the few inherently serial steps (list bookkeeping, assignment problems)
 // run on one thread per problem.  With Ctx = HostCtx (one "thread", sync = no-op) the same source runs
@@ -65,6 +66,7 @@ struct DevCfg {
     int64_t off_hdr, off_meta, off_view, off_hist, off_vel, off_nv, off_init, off_raw, off_margin, seq_bytes;
     // per-sequence working arena: [SeqShared<K> (compile-time capacity class K)][detection buffers][raw pose]
     int caps;                                // capacity class (CAPS_*), chosen from V, D, J, max_trk
+    int convoy;                              // one-warp groups of a CTA start every frame together (instruction-cache locality)
     int nbuf;                                // detection buffers: 2 = next frame staged during the current one
     int frame_floats;                        // V * D * J * 3, padded to a multiple of 4
     int a_dets, a_raw;                       // byte offsets of the run-time sized tail (a_raw < 0: raw pose in HBM scratch)
@@ -291,11 +293,12 @@ struct HostCtx {
     inline int tid() const { return 0; }
     inline int nthreads() const { return 1; }
     inline void sync() const {}
+    inline void phase_sync() const {}
     inline void atomic_inc(int* p) const { *p += 1; }
     inline long long clock() const { return 0; }
 };
 struct NoHook {
-    inline void dets_released() const {}
+    PAM_HD void dets_released() const {}
 };
 
 #if defined(PAM_MARGIN)
@@ -569,6 +572,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
     if (hdr.status != SEQ_OK) {   // uniform: status only changes between syncs
         if (ctx.tid() == 0 && out.count) *out.count = 0;
         hook.dets_released();
+        for (int k = 0; k < 7; ++k) ctx.phase_sync();     // keep in step with the other sequences of a convoy
         return;
     }
     const int n = hdr.ntracks;
@@ -604,7 +608,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
         int* mw = (int*)sh.match;                     // t2d and d2t, contiguous
         PAM_FOR_REV(i, (int)(sizeof(sh.match) / 4)) mw[i] = -1;
     }
-    ctx.sync();
+    ctx.phase_sync();
 
     // ---- phase 2: track x detection affinity (IterativeTracker.py:139-149) ----------------------
     PAM_FOR(it, V * n * D) {
@@ -637,7 +641,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
         if (a > 0.0) PAM_NOTE(MG_ASSIGN, a);
         sh.aff[cam][i][d] = a;
     }
-    ctx.sync();
+    ctx.phase_sync();
 
     // ---- phase 3: one assignment problem per camera (IterativeTracker.py:150-160) ---------------
     // Only pairs with affinity > 0 are ever accepted.  When the positive entries of a camera's
@@ -673,7 +677,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
             sh.conflict[cam] = 1; fs.any_conflict = 1;
         }
     }
-    ctx.sync();
+    ctx.phase_sync();
     if (fs.any_conflict) {   // uniform
         PAM_FOR(cam, V) {
             if (!sh.conflict[cam]) continue;
@@ -755,7 +759,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
         sh.believe[cam][d] = b;
         sh.um_flag[cam][d] = (b > c.conf_thr) ? 1 : 0;
     }
-    ctx.sync();
+    ctx.phase_sync();
 
     // ---- phase 5: per (track, joint): part-aware view filter + DLT (IterativeTracker.py:337-369);
     //      unmatched lists ---------------------------------------------------------------------
@@ -786,7 +790,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
             if (sh.um_flag[cam][d]) sh.um[cam][k++] = (signed char)d;
         sh.um_n[cam] = (signed char)k;
     }
-    ctx.sync();
+    ctx.phase_sync();
     // new-track initialisation has something to do when two cameras hold unmatched detections (a hypothesis
     // needs views from two cameras to become a track, hypothesis.size() > 1); every thread evaluates it
     // (uniform), so the staged detections can be released right here on the frames that do not need them
@@ -895,7 +899,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
         PAM_NOUNROLL for (int i = 0; i < n; ++i) sh.out_row[i] = track_reported(c, sq, i) ? (signed char)(k++) : (signed char)-1;
         if (out.count) *out.count = k;
     }
-    ctx.sync();
+    ctx.phase_sync();
     {
         const double* const rawb = sq.raw_;
         PAM_FOR(it, n * J) {
@@ -948,7 +952,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
             fs.hyp_n = n0;
         }
     }
-    ctx.sync();
+    ctx.phase_sync();
     // 7b, one thread: compaction of the track list, only on the frames a track was deleted
     if (ctx.tid() == 0) {
         if (fs.any_deleted) {

@@ -74,3 +74,13 @@ def gather_results(out: Dict[str, "object"], dst: int = 0):
         if rank == dst:
             res[k] = torch.stack(bufs)
     return res if rank == dst else None
+
+
+def all_gather_results(out: Dict[str, "object"], gathered: Dict[str, "object"]):
+    """One collective per result tensor: the fixed-stride blocks ``count/ids/joints`` of every rank into
+    ``gathered[k]`` of shape ``(world,) + out[k].shape`` on every rank (NCCL all-gather over NVLink on the B200
+    box).  Device resident on both sides, asynchronous on the current stream."""
+    import torch.distributed as dist
+    for k, buf in gathered.items():
+        dist.all_gather_into_tensor(buf.view(-1), out[k].reshape(-1))
+    return gathered

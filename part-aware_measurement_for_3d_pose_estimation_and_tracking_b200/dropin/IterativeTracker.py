@@ -1,9 +1,11 @@
 """GPU-backed ``IterativeTracker`` with the reference's call surface
 (src/tracking/IterativeTracker.py:21-50, 115-180, 182-287).
 
-``tracking()`` runs ONE frame of ONE sequence through ``pam_track_sequences_host`` (H2D of the
-frame's detections, one kernel launch, D2H of the reported tracks); the tracker state stays in HBM
-between calls.  ``.tracks`` reads the state back on demand and exposes the IterTrack read surface."""
+``tracking()`` hands ONE frame of ONE sequence to the resident kernel of the library's stream mode
+(``pam_stream_step``: the detections are written into a pinned, device-mapped slot, the kernel keeps the
+tracker state on chip and writes the reported tracks back; no launch, no copies, no state round trip per
+call).  ``.tracks`` reads the state back on demand (this parks the resident kernel; the next ``tracking()``
+call restarts it) and exposes the IterTrack read surface."""
 import time as _time
 
 import numpy as np
@@ -52,8 +54,15 @@ class IterativeTracker(object):
     #: COCO-17 (src/tracking/IterativeTracker.py:382, :145); overridable for other skeletons
     ARM_JOINTS = (9, 10)
     MIN_VALID_JOINTS = 10
-    MAX_TRACKS = 16
-    MAX_DETECTIONS = 16
+    #: capacities of the device-resident state (the reference has none): track slots per sequence (<= 32) and
+    #: detections per camera and frame (<= 16).  A frame that needs more DROPS the excess (the new track is not
+    #: created / the detection is ignored), tracking goes on and a PamCapacityWarning is issued once.
+    MAX_TRACKS = 12
+    MAX_DETECTIONS = 8
+    #: The device path ingests detections as float32 (the reference's come from a float32 pose net and are
+    #: float32-exact).  True: a float64 value that float32 cannot represent raises ValueError instead of being
+    #: rounded silently (parity with the reference is only claimed for representable input).
+    STRICT_FLOAT32 = True
 
     def __init__(self, args):
         self.args = args
@@ -68,6 +77,9 @@ class IterativeTracker(object):
         self._trk = None
         self._cams = None
         self._tracks_cache = None
+        self._stream = None
+        self._fresh = True
+        self._warned = False
 
     def track_restart(self):
         self._pending = None
@@ -85,37 +97,53 @@ class IterativeTracker(object):
             self._trk = _tracker.SequenceTracker(self._cams, self.args, 1, self.MAX_DETECTIONS, self.MAX_TRACKS,
                                                  self.ARM_JOINTS, self.MIN_VALID_JOINTS)
             self._fresh = True
-            V, D, J, MT = len(self._cams), self.MAX_DETECTIONS, self.num_joints, self.MAX_TRACKS
-            self._dets = np.zeros((1, 1, V, D, J, 3), np.float32)
-            self._counts = np.zeros((1, 1, V), np.int32)
-            self._out = dict(count=np.zeros((1, 1), np.int32), ids=np.zeros((1, 1, MT), np.int32),
-                             joints=np.zeros((1, 1, MT, J, 3), np.float32), nviews=np.zeros((1, 1, MT, J), np.uint8),
-                             assoc=np.zeros((1, 1, V, D), np.int32))
+            self._stream = None
+            self._cycle_s = 1.0 / (1e3 * max(1, self._trk.sm_clock_khz()))
+        if self._fresh or self._stream is None:
+            self._stream = self._trk.open_stream(fresh=self._fresh)      # resident kernel, state on chip
+            self._fresh = False
 
     def tracking(self, frame_id, camera_list, frame_list, boxes_list, detections_list, build3D='TopDown'):
+        """One frame (src/tracking/IterativeTracker.py:115-180).  Returns ``(asso_time, update_time, init_time)`` in
+        seconds, measured on the device (SM cycle counters around the same three blocks the reference times)."""
         assert build3D == 'SVD', "Please modify BUILD3D to SVD when PERSON_MATCHER == Iterative"
         self.frame_list = frame_list
         self.build3D = build3D
         self.cam_num = len(camera_list)
         self._ensure(camera_list)
-        t0 = _time.time()
-        self._counts[:] = 0
-        for c, dets in enumerate(detections_list):
-            m = len(dets)
-            if m > self.MAX_DETECTIONS:
-                raise ValueError(f"camera {c}: {m} detections exceed MAX_DETECTIONS={self.MAX_DETECTIONS}")
+        st = self._stream
+        dets, counts = st.dets, st.counts
+        maxd, strict = self.MAX_DETECTIONS, self.STRICT_FLOAT32
+        for c, d in enumerate(detections_list):
+            m = len(d)
+            if m > maxd:
+                self._warn(f"camera {c}: {m} detections, the first {maxd} are used (MAX_DETECTIONS)")
+                d, m = d[:maxd], maxd
             if m:
-                self._dets[0, 0, c, :m] = np.asarray(dets, dtype=np.float32)
-            self._counts[0, 0, c] = m
-        self._trk.run_host(self._dets, self._counts, frame0=int(frame_id), fresh=self._fresh, nviews=True, assoc=True,
-                           out=self._out)
-        self._fresh = False
+                dst = dets[c, :m]
+                dst[...] = d                              # float64 -> float32
+                if strict and not np.array_equal(dst, d):
+                    raise ValueError(f"camera {c}: detections are not float32-representable; the device path would round "
+                                     "them (set IterativeTracker.STRICT_FLOAT32 = False to accept the rounding)")
+            counts[c] = m
+        st.step(int(frame_id))
         self._tracks_cache = None
-        k = int(self._out["count"][0, 0])
-        self.last_ids = self._out["ids"][0, 0, :k].copy()
-        self.last_joints = self._out["joints"][0, 0, :k].astype(np.float64)
-        self._pending = (frame_id, camera_list, boxes_list, detections_list, self._out["assoc"][0, 0].copy())
-        return _time.time() - t0, 0.0, 0.0
+        k = int(st.count[0])
+        self.last_ids = st.ids[:k].copy()
+        self.last_joints = st.joints[:k].astype(np.float64)
+        self.last_nviews = st.nviews[:k].copy()
+        self._pending = (frame_id, camera_list, boxes_list, detections_list, st.assoc.copy())
+        if st.status[0] and not self._warned:
+            self._warn("a frame needed more track slots / hypotheses / detections than configured "
+                       f"(MAX_TRACKS={self.MAX_TRACKS}, MAX_DETECTIONS={self.MAX_DETECTIONS}); the excess was dropped")
+        tm, cs = st.timing, self._cycle_s
+        return tm[0] * cs, tm[1] * cs, tm[2] * cs
+
+    def _warn(self, msg):
+        if not self._warned:
+            import warnings
+            warnings.warn(msg, _tracker.PamCapacityWarning, stacklevel=3)
+            self._warned = True
 
     @property
     def unmatched(self):

@@ -199,6 +199,17 @@ class SequenceTracker:
         self._host_S = S
         return out
 
+    # -- stream mode: one frame per call through the resident kernel -----------------------------
+    def open_stream(self, fresh: bool = True) -> "FrameStream":
+        """Start the resident per-frame kernel of this tracker's (single) sequence and return the zero-copy
+        views of its command / result slot (``include/pam.h``: pam_stream_open)."""
+        assert self.S == 1, "stream mode tracks one sequence"
+        _check(self.lib, self.handle, self.lib.pam_stream_open(self.handle, 1 if fresh else 0))
+        self._host_S = 1
+        if fresh:
+            self.next_frame = 0
+        return FrameStream(self)
+
     # -- state read-back (IterTrack read surface) ---------------------------------------------
     def read_state(self, host_path: bool = False):
         """Parse the tracker state of every sequence: list (per sequence) of track dicts in
@@ -213,6 +224,42 @@ class SequenceTracker:
             self._torch().cuda.synchronize(self.device)
             blob = self._state.cpu().numpy()
         return parse_state(blob, S, L, self.cfg)
+
+
+class FrameStream:
+    """numpy views over the pinned, device-mapped slot of the resident kernel: write ``dets (V,D,J,3)`` /
+    ``counts (V,)``, call ``step(frame_id)``, read ``count[0]``, ``ids``, ``joints``, ``nviews``, ``assoc``,
+    ``timing`` (SM cycles: association, update, initialisation, total)."""
+
+    def __init__(self, trk: "SequenceTracker"):
+        self.trk = trk
+        v = _capi.PamStreamViews()
+        _check(trk.lib, trk.handle, trk.lib.pam_stream_buffers(trk.handle, C.byref(v)))
+        c = trk.cfg
+        V, D, J, MT = c.num_cameras, c.max_detections, c.num_joints, c.max_tracks
+
+        def view(ptr, ctype, shape):
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=shape)
+
+        self.dets = view(v.dets, C.c_float, (V, D, J, 3))
+        self.counts = view(v.counts, C.c_int32, (V,))
+        self.count = view(v.out_count, C.c_int32, (1,))
+        self.ids = view(v.out_ids, C.c_int32, (MT,))
+        self.joints = view(v.out_joints, C.c_float, (MT, J, 3))
+        self.nviews = view(v.out_nviews, C.c_uint8, (MT, J))
+        self.assoc = view(v.out_assoc, C.c_int32, (V, D))
+        self.timing = view(v.out_timing, C.c_int32, (4,))
+        self.status = view(v.out_status, C.c_int32, (1,))
+        self._step = trk.lib.pam_stream_step
+        self._handle = trk.handle
+
+    def step(self, frame_id: int):
+        rc = self._step(self._handle, frame_id)
+        if rc != 0:
+            _check(self.trk.lib, self.trk.handle, rc)
+
+    def close(self):
+        _check(self.trk.lib, self.trk.handle, self.trk.lib.pam_stream_close(self.trk.handle))
 
 
 def parse_state(blob: np.ndarray, S: int, L, cfg):

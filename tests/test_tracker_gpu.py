@@ -113,22 +113,19 @@ def test_capacity_overflow_is_reported():
 
 
 @pytest.mark.parametrize("env", [
-    {"PAM_TRACK_SHAPE": "1:8:64"},      # one warp per sequence, 8 sequences per CTA, 64 registers (32 sequences per SM)
-    {"PAM_TRACK_SHAPE": "1:7:72"},      # 28 sequences per SM
-    {"PAM_TRACK_SHAPE": "1:8:80"},      # 24 sequences per SM
-    {"PAM_TRACK_SHAPE": "1:3:128"},     # one warp per sequence, full register budget, ragged last CTA
+    {"PAM_TRACK_SHAPE": "1:8:128"},     # one warp per sequence, 8 sequences per CTA, frames of the CTA started together
+    {"PAM_TRACK_SHAPE": "1:12:80"},     # 24 sequences per SM
+    {"PAM_TRACK_SHAPE": "1:8:80", "PAM_TRACK_CONVOY": "2"},   # ... every phase together
+    {"PAM_TRACK_SHAPE": "1:3:128", "PAM_TRACK_CONVOY": "0"},  # free running, ragged last CTA
     {"PAM_TRACK_SHAPE": "1:8:80:0"},    # one warp per sequence with the latency flavour of the working set
-    {"PAM_TRACK_SHAPE": "2:4:64"},      # two warps per sequence (named barriers), 4 sequences per CTA
-    {"PAM_TRACK_SHAPE": "2:2:80"},
-    {"PAM_TRACK_SHAPE": "2:2:128:1"},   # ... with one detection buffer and the raw pose in HBM scratch
     {"PAM_TRACK_SHAPE": "3:1:80"},      # three warps, one sequence per CTA (round-1 shape)
-    {"PAM_TRACK_SHAPE": "3:2:80:1"},
-    {"PAM_TRACK_SHAPE": "4:1:64"},
+    {"PAM_TRACK_SHAPE": "3:1:80:1"},    # ... with one detection buffer and the raw pose in HBM scratch
     {"PAM_TRACK_SHAPE": "4:1:128"},     # single-stream default
     {"PAM_TRACK_SHAPE": "8:1:128"},
     # Panoptic-sized working set (12 track slots): capacity class "mid"
+    {"PAM_TRACK_SHAPE": "1:6:128", "max_tracks": "12"},
     {"PAM_TRACK_SHAPE": "1:8:80", "max_tracks": "12"},
-    {"PAM_TRACK_SHAPE": "2:2:80", "max_tracks": "12"},
+    {"PAM_TRACK_SHAPE": "3:1:80", "max_tracks": "12"},
     {"PAM_TRACK_SHAPE": "8:1:128", "max_tracks": "12"},
     # largest working set (32 track slots): capacity class "max"
     {"PAM_TRACK_SHAPE": "1:2:128", "max_tracks": "32"},

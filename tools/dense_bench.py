@@ -7,8 +7,9 @@ import numpy as np, torch
 import pam_b200
 from pam_b200 import synth, camera, ops
 
-PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
-    if os.path.exists("MEASURED_PEAKS.json") else 6650.0
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PEAK = json.load(open(os.path.join(_ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] \
+    if os.path.exists(os.path.join(_ROOT, "MEASURED_PEAKS.json")) else 6650.0
 st = synth.make_stream("dense", 0, 2, miss_prob=0.0, outlier_prob=0.01)
 sh = st.shape
 V, P, J = sh.V, sh.P, sh.J

@@ -49,6 +49,9 @@ cache = {}
 for cfg in a.configs:
     shp, S = cfg.split("@")
     S = int(S)
+    # "<shape>/c": the sequences of a CTA start every frame together; "/p": ... every phase together
+    os.environ["PAM_TRACK_CONVOY"] = "1" if shp.endswith("/c") else ("2" if shp.endswith("/p") else "0")
+    shp = shp[:-2] if shp[-2:] in ("/c", "/p") else shp
     if shp == "auto":
         os.environ.pop("PAM_TRACK_SHAPE", None)
     else:
