@@ -176,13 +176,14 @@ int pam_track_host_status(pam_handle* h, int32_t S, int32_t* h_status);
 /* ---- stream mode: the reference's call pattern, one tracking() call per frame (ivclabpose.py:257) ----------
  * ONE sequence.  pam_stream_open starts a resident kernel (one CTA) that keeps the tracker state on chip and polls
  * a command word in pinned, device-mapped host memory; pam_stream_buffers returns HOST pointers into that slot:
- * the caller writes the frame's detections / counts there (same layout as one frame of pam_track_sequences),
+ * the caller writes the frame's detections (PACKED: cameras back to back, no padding) and counts there,
  * calls pam_stream_step(frame_id) -- which returns when the results are in the slot -- and reads count / ids /
  * joints / nviews / assoc / timing from it.  No launch, no copies, no state round trip per frame.  The kernel
  * leaves after about one idle second (the state is stored; the next step starts it again).  The tracker state is
  * the one of the _host path (S = 1): pam_track_state_to_host and pam_track_sequences_host close the stream first. */
 typedef struct pam_stream_views {
-    float* dets;            /* [V][D][J][3]            in  */
+    float* dets;            /* [sum of counts][J][3]   in: the detections of camera 0, 1, ... back to back
+                               (room for V * D of them)                                                   */
     int32_t* counts;        /* [V]                     in  */
     int32_t* out_count;     /* [1]                     out */
     int32_t* out_ids;       /* [max_tracks]                */
@@ -194,7 +195,9 @@ typedef struct pam_stream_views {
 } pam_stream_views;
 int pam_stream_open(pam_handle* h, int32_t fresh);
 int pam_stream_buffers(pam_handle* h, pam_stream_views* out);
-int pam_stream_step(pam_handle* h, int32_t frame_id);
+int pam_stream_step(pam_handle* h, int32_t frame_id);        /* = submit + wait */
+int pam_stream_submit(pam_handle* h, int32_t frame_id);      /* returns at once; host work may overlap the frame */
+int pam_stream_wait(pam_handle* h);
 int pam_stream_close(pam_handle* h);
 
 /* Copy the internal state of the _host path (S sequences) to a host buffer of S*seq_bytes. */

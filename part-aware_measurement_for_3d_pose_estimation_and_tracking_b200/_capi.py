@@ -82,6 +82,8 @@ _PROTOTYPES = [
     ("pam_stream_open", C.c_int, [_P, C.c_int32]),
     ("pam_stream_buffers", C.c_int, [_P, C.POINTER(PamStreamViews)]),
     ("pam_stream_step", C.c_int, [_P, C.c_int32]),
+    ("pam_stream_submit", C.c_int, [_P, C.c_int32]),
+    ("pam_stream_wait", C.c_int, [_P]),
     ("pam_stream_close", C.c_int, [_P]),
     ("pam_launch_count", C.c_int64, [_P]),
     ("pam_project_points", C.c_int, [_P, _P, C.c_int32, _P, _P]),
@@ -124,3 +126,26 @@ def load_library(path: str | None = None):
     if path is None:
         _lib = lib
     return lib
+
+
+_fast = None
+
+
+def load_pyfast():
+    """The CPython packing helper of the per-frame drop-in path (csrc/pam_pyfast.c), bound to this library's
+    pam_stream_submit / pam_stream_wait; None when it has not been built (the drop-in then packs with numpy)."""
+    global _fast
+    if _fast is None:
+        import importlib.util
+        import sysconfig
+        path = os.path.join(_HERE, "csrc", "pam_pyfast" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+        if not os.path.exists(path):
+            _fast = False
+            return None
+        spec = importlib.util.spec_from_file_location("pam_pyfast", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        lib = load_library()
+        mod.bind(C.cast(lib.pam_stream_submit, C.c_void_p).value, C.cast(lib.pam_stream_wait, C.c_void_p).value)
+        _fast = mod
+    return _fast or None

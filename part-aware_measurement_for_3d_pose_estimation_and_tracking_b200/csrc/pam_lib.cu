@@ -233,17 +233,15 @@ k_track_stream(const DevCfg c, const CamConst cc, char* __restrict__ state, char
     char* arena = smem + CAMB;
     load_cameras(threadIdx.x, NT, c, cam, cc);
     SeqShared<K>& sh = *(SeqShared<K>*)arena;
-    __shared__ int s_cmd, s_frame;
+    __shared__ int s_cmd, s_frame, s_tail;
+    __shared__ unsigned s_cnt8[2];
     __syncthreads();
     Seq<K> sq;
     sq.bind(c, arena, cam, state);
     load_state(ctx, c, sq);
-    const int nfl = c.V * c.D * c.J * 3;
     float* dbuf = (float*)(arena + c.a_dets);
     int* cbuf = &sh.cnt[0][0];
-    volatile int* h_cmd = (volatile int*)(slot + so.o_cmd);
-    const volatile float* h_dets = (const volatile float*)(slot + so.o_dets);
-    const volatile int* h_counts = (const volatile int*)(slot + so.o_counts);
+    const char* h_cmd = slot + so.o_cmd;   // 16 bytes: sequence number, frame id, per-camera counts (one byte each)
     FrameOut o;
     o.count = (int*)(slot + so.o_count); o.ids = (int*)(slot + so.o_ids); o.joints = (float*)(slot + so.o_joints);
     o.nviews = (unsigned char*)(slot + so.o_nv); o.assoc = (int*)(slot + so.o_assoc); o.timing = (int*)(slot + so.o_timing);
@@ -254,45 +252,85 @@ k_track_stream(const DevCfg c, const CamConst cc, char* __restrict__ state, char
         if (threadIdx.x == 0) {
             const long long t0 = clock64();
             int cmd;
+            unsigned w0, w1, w2, w3;
             for (;;) {
-                cmd = *h_cmd;
+                // one 16-byte PCIe read: sequence number, frame id and the per-camera counts together
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "l"(h_cmd) : "memory");
+                cmd = (int)w0;
                 if (cmd != last_seq) break;
                 if (clock64() - t0 > idle_limit_cycles) { cmd = STREAM_CMD_EXIT; break; }    // nobody is calling: free the SM
             }
             s_cmd = cmd;
-            if (cmd != STREAM_CMD_EXIT) s_frame = *(volatile int*)(slot + so.o_frame);
+            s_frame = (int)w1;
+            s_cnt8[0] = w2; s_cnt8[1] = w3;
         }
         ctx.sync();
+        const long long tq0 = clock64();
         const int cmd = s_cmd;
         if (cmd == STREAM_CMD_EXIT) break;
         last_seq = cmd;
         const int frame = s_frame;
-        // this frame's detections: host memory -> shared memory, all threads, 16 bytes per request when aligned
-        if ((nfl & 3) == 0) {
-            const volatile float4* src = (const volatile float4*)h_dets;
-            float4* dst = (float4*)dbuf;
-            PAM_NOUNROLL for (int i = threadIdx.x; i < nfl / 4; i += NT) {
-                float4 v;
-                v.x = src[i].x; v.y = src[i].y; v.z = src[i].z; v.w = src[i].w;
-                dst[i] = v;
+        // this frame's detections: host memory -> shared memory.  The host packs the detections of all cameras back
+        // to back ([sum of counts][J][3], what one numpy.concatenate produces); the rows are spread to the padded
+        // [V][D][J][3] layout here.  Uncached loads (ld.global.cv: the slot is rewritten between frames), eight in
+        // flight per thread so that the whole frame costs ONE PCIe round trip.
+        {
+            int off[PAM_MAX_V + 1];
+            int acc = 0;
+#pragma unroll
+            for (int v = 0; v < PAM_MAX_V; ++v) {
+                off[v] = acc;
+                int m = (v < c.V) ? (int)((s_cnt8[v >> 2] >> ((v & 3) * 8)) & 0xffu) : 0;
+                m = m > c.D ? c.D : m;
+                if (threadIdx.x == v) cbuf[v] = m;
+                acc += m;
             }
-        } else {
-            PAM_NOUNROLL for (int i = threadIdx.x; i < nfl; i += NT) dbuf[i] = h_dets[i];
+            off[PAM_MAX_V] = acc;
+            const int row = c.J * 3;                          // floats per detection
+            const int total = acc * row;
+            const float inv_row = 1.0f / (float)row;
+            const float* src = (const float*)(slot + so.o_dets);
+            PAM_NOUNROLL for (int base = 0; base < total; base += NT * 8) {
+                float v8[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = base + k * NT + (int)threadIdx.x;
+                    v8[k] = (i < total) ? __ldcv(src + i) : 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = base + k * NT + (int)threadIdx.x;
+                    if (i >= total) continue;
+                    const int r = fast_div(i, inv_row), e = i - r * row;
+                    int v = 0;
+#pragma unroll
+                    for (int q = 1; q < PAM_MAX_V; ++q) v += (r >= off[q] && q < c.V) ? 1 : 0;
+                    dbuf[((v * c.D) + (r - off[v])) * row + e] = v8[k];
+                }
+            }
         }
-        if (threadIdx.x < c.V) cbuf[threadIdx.x] = h_counts[threadIdx.x];
         ctx.sync();
         // stale views are read from the persisted copies (gin_frame0 = frame: only this frame's views count as
         // "inside the launch"), which persist_views refreshes after every frame
+        const long long tq1 = clock64();
         frame_step(ctx, c, sq, frame, dbuf, cbuf, o, dbuf, frame, hook);
         ctx.sync();
-        persist_views(ctx, c, sq, dbuf, frame, dbuf, 0);
-        __threadfence_system();
-        ctx.sync();
+        const long long tq2 = clock64();
         if (threadIdx.x == 0) {
             *(volatile int*)(slot + so.o_status) = sh.hdr.status | (sh.hdr.warn << 8);
-            __threadfence_system();
-            *(volatile int*)(slot + so.o_done) = cmd;
+            // protocol timing (SM cycles): input transfer, frame, and -- one frame late -- result write-back + persist
+            int* tm = (int*)(slot + so.o_timing);
+            tm[4] = (int)(tq1 - tq0); tm[5] = (int)(tq2 - tq1); tm[6] = s_tail;
         }
+        // results first (every writer fences its own stores), then the completion word; the views of this frame
+        // are persisted while the host already reads the results
+        __threadfence_system();
+        ctx.sync();
+        if (threadIdx.x == 0) *(volatile int*)(slot + so.o_done) = cmd;
+        const long long tq3 = clock64();
+        persist_views(ctx, c, sq, dbuf, frame, dbuf, 0);
+        ctx.sync();
+        if (threadIdx.x == 0) s_tail = (int)(tq3 - tq2) | ((int)(clock64() - tq3) << 16);
     }
     store_state(ctx, c, sq);
     ctx.sync();
@@ -342,7 +380,7 @@ struct pam_handle {
     char* st_slot_dev = nullptr;
     StreamSlot st_so{};
     bool st_running = false;
-    int st_seq = 0;
+    int st_seq = 0, st_frame = 0;
     cudaStream_t st_stream = nullptr;
     char* zc = nullptr;        // pinned, device-mapped staging of the small-job path
     size_t zc_cap = 0;
@@ -865,7 +903,7 @@ static int stream_launch(pam_handle* h) {
     const size_t smem = track_smem_bytes(c, 1);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     *(volatile int*)(h->st_slot + h->st_so.o_done) = 0;
-    *(volatile int*)(h->st_slot + h->st_so.o_cmd) = 0;
+    *(volatile unsigned long long*)(h->st_slot + h->st_so.o_cmd) = 0ull;
     h->st_seq = 0;
     const long long idle = (long long)h->clock_khz * 1000;        // about one second of SM cycles
     fn<<<1, c.caps == CAPS_MAX ? 256 : 128, smem, h->st_stream>>>(c, h->cc, (char*)h->ws_state.p, h->st_slot_dev, h->st_so, idle);
@@ -894,11 +932,11 @@ int pam_stream_open(pam_handle* h, int32_t fresh) {
         StreamSlot so;
         int o = 0;
         auto take = [&](size_t bytes) { const int at = o; o += (int)((bytes + 127) / 128 * 128); return at; };
-        so.o_cmd = take(4); so.o_frame = take(4); so.o_counts = take(4 * PAM_MAX_V);
+        so.o_cmd = take(16); so.o_frame = so.o_cmd + 4; so.o_counts = take(4 * PAM_MAX_V);
         so.o_dets = take((size_t)c.V * c.D * c.J * 3 * 4);
         so.o_done = take(4); so.o_count = take(4); so.o_ids = take((size_t)c.max_trk * 4);
         so.o_joints = take((size_t)c.max_trk * c.J * 3 * 4); so.o_nv = take((size_t)c.max_trk * c.J);
-        so.o_assoc = take((size_t)c.V * c.D * 4); so.o_timing = take(16); so.o_status = take(4);
+        so.o_assoc = take((size_t)c.V * c.D * 4); so.o_timing = take(32); so.o_status = take(4);
         so.bytes = o;
         CK(cudaHostAlloc((void**)&h->st_slot, (size_t)o, cudaHostAllocMapped));
         memset(h->st_slot, 0, (size_t)o);
@@ -919,24 +957,43 @@ int pam_stream_buffers(pam_handle* h, pam_stream_views* v) {
     return PAM_OK;
 }
 
-int pam_stream_step(pam_handle* h, int32_t frame_id) {
+int pam_stream_submit(pam_handle* h, int32_t frame_id) {
     if (!h || !h->st_slot) return fail(h, PAM_E_INVALID, "stream not open");
-    volatile int* cmd = (volatile int*)(h->st_slot + h->st_so.o_cmd);
+    volatile int* done = (volatile int*)(h->st_slot + h->st_so.o_done);
+    if (!h->st_running || *done == STREAM_CMD_EXIT) {        // the kernel left after an idle second: start it again
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->st_stream));
+        h->st_running = false;
+        int rc = stream_launch(h);
+        if (rc != PAM_OK) return rc;
+    }
+    int seq = h->st_seq + 1;
+    if (seq <= 0) seq = 1;
+    h->st_seq = seq;
+    h->st_frame = frame_id;
+    // the command line (16 bytes, one PCIe read for the kernel): per-camera counts as bytes first, then sequence
+    // number + frame id in ONE 8-byte store
+    {
+        const int32_t* cnt = (const int32_t*)(h->st_slot + h->st_so.o_counts);
+        unsigned long long packed = 0ull;
+        for (int v = 0; v < h->dc.V; ++v) {
+            int m = cnt[v];
+            m = m < 0 ? 0 : (m > 255 ? 255 : m);
+            packed |= (unsigned long long)m << (8 * v);
+        }
+        *(volatile unsigned long long*)(h->st_slot + h->st_so.o_cmd + 8) = packed;
+    }
+    std::atomic_thread_fence(std::memory_order_release);     // inputs before the command word
+    *(volatile unsigned long long*)(h->st_slot + h->st_so.o_cmd) =
+        (unsigned long long)(unsigned)seq | ((unsigned long long)(unsigned)frame_id << 32);
+    return PAM_OK;
+}
+
+int pam_stream_wait(pam_handle* h) {
+    if (!h || !h->st_slot) return fail(h, PAM_E_INVALID, "stream not open");
     volatile int* done = (volatile int*)(h->st_slot + h->st_so.o_done);
     for (int attempt = 0; attempt < 3; ++attempt) {
-        if (!h->st_running || *done == STREAM_CMD_EXIT) {        // the kernel left after an idle second: start it again
-            CK(cudaSetDevice(h->device));
-            CK(cudaStreamSynchronize(h->st_stream));
-            h->st_running = false;
-            int rc = stream_launch(h);
-            if (rc != PAM_OK) return rc;
-        }
-        *(volatile int*)(h->st_slot + h->st_so.o_frame) = frame_id;
-        int seq = h->st_seq + 1;
-        if (seq <= 0) seq = 1;
-        h->st_seq = seq;
-        std::atomic_thread_fence(std::memory_order_release);     // inputs before the command word
-        *cmd = seq;
+        const int seq = h->st_seq;
         const auto t0 = std::chrono::steady_clock::now();
         for (int spin = 0;; ++spin) {
             const int d = *done;
@@ -955,15 +1012,22 @@ int pam_stream_step(pam_handle* h, int32_t frame_id) {
                 }
             }
         }
+        int rc = pam_stream_submit(h, h->st_frame);              // the inputs are still in the slot
+        if (rc != PAM_OK) return rc;
     }
     return fail(h, PAM_E_INTERNAL, "resident kernel keeps exiting");
+}
+
+int pam_stream_step(pam_handle* h, int32_t frame_id) {
+    int rc = pam_stream_submit(h, frame_id);
+    return rc != PAM_OK ? rc : pam_stream_wait(h);
 }
 
 int pam_stream_close(pam_handle* h) {
     if (!h) return PAM_OK;
     if (!h->st_running) return PAM_OK;
     CK(cudaSetDevice(h->device));
-    *(volatile int*)(h->st_slot + h->st_so.o_cmd) = STREAM_CMD_EXIT;
+    *(volatile unsigned long long*)(h->st_slot + h->st_so.o_cmd) = 0xffffffffull;      // STREAM_CMD_EXIT
     CK(cudaStreamSynchronize(h->st_stream));       // the kernel stores the tracker state before it leaves
     h->st_running = false;
     return PAM_OK;

@@ -10,7 +10,7 @@ import time as _time
 
 import numpy as np
 
-from _pkg import camera as _camera, tracker as _tracker
+from _pkg import camera as _camera, tracker as _tracker, capi as _capi
 from calculate import get_believe
 
 
@@ -78,6 +78,7 @@ class IterativeTracker(object):
         self._cams = None
         self._tracks_cache = None
         self._stream = None
+        self._cam_list_ref = None
         self._fresh = True
         self._warned = False
 
@@ -89,6 +90,8 @@ class IterativeTracker(object):
         self._fresh = True
 
     def _ensure(self, camera_list):
+        if camera_list is self._cam_list_ref and not self._fresh and self._stream is not None:
+            return                                     # same list object as last frame: nothing to set up
         if self._trk is None or self._cams is None or len(camera_list) != len(self._cams) or \
                 any(a is not b for a, b in zip(camera_list, self._cams)):
             if self._trk is not None:
@@ -99,8 +102,14 @@ class IterativeTracker(object):
             self._fresh = True
             self._stream = None
             self._cycle_s = 1.0 / (1e3 * max(1, self._trk.sm_clock_khz()))
+        self._cam_list_ref = camera_list
         if self._fresh or self._stream is None:
             self._stream = self._trk.open_stream(fresh=self._fresh)      # resident kernel, state on chip
+            st = self._stream
+            self._fast = _capi.load_pyfast()
+            self._handle_addr = self._trk.handle.value
+            self._packed_addr, self._counts_addr = st.packed.ctypes.data, st.counts.ctypes.data
+            self._row = st.packed.shape[1] * 3
             self._fresh = False
 
     def tracking(self, frame_id, camera_list, frame_list, boxes_list, detections_list, build3D='TopDown'):
@@ -112,32 +121,59 @@ class IterativeTracker(object):
         self.cam_num = len(camera_list)
         self._ensure(camera_list)
         st = self._stream
-        dets, counts = st.dets, st.counts
-        maxd, strict = self.MAX_DETECTIONS, self.STRICT_FLOAT32
-        for c, d in enumerate(detections_list):
-            m = len(d)
-            if m > maxd:
-                self._warn(f"camera {c}: {m} detections, the first {maxd} are used (MAX_DETECTIONS)")
-                d, m = d[:maxd], maxd
-            if m:
-                dst = dets[c, :m]
-                dst[...] = d                              # float64 -> float32
-                if strict and not np.array_equal(dst, d):
-                    raise ValueError(f"camera {c}: detections are not float32-representable; the device path would round "
-                                     "them (set IterativeTracker.STRICT_FLOAT32 = False to accept the rounding)")
-            counts[c] = m
-        st.step(int(frame_id))
         self._tracks_cache = None
-        k = int(st.count[0])
-        self.last_ids = st.ids[:k].copy()
-        self.last_joints = st.joints[:k].astype(np.float64)
-        self.last_nviews = st.nviews[:k].copy()
-        self._pending = (frame_id, camera_list, boxes_list, detections_list, st.assoc.copy())
+        self._pending = (frame_id, camera_list, boxes_list, detections_list)
+        fast = self._fast
+        if fast is not None:
+            # one call: float64 -> float32 packing into the mapped slot (with the representability check), submit, wait
+            try:
+                rc, flags = fast.track_frame(self._handle_addr, int(frame_id), detections_list, self._packed_addr,
+                                             self._counts_addr, st.V, st.D, self._row, 1 if self.STRICT_FLOAT32 else 0)
+            except TypeError:
+                fast = None                # python lists instead of arrays etc.: numpy path below
+            else:
+                if rc != 0:
+                    _tracker._check(self._trk.lib, self._trk.handle, rc)
+                if flags & 2 and self.STRICT_FLOAT32:
+                    raise ValueError("detections are not float32-representable; the device path would round them "
+                                     "(set IterativeTracker.STRICT_FLOAT32 = False to accept the rounding)")
+                if flags & 1:
+                    self._warn(f"more than MAX_DETECTIONS={self.MAX_DETECTIONS} detections in a camera: the first "
+                               f"{self.MAX_DETECTIONS} were used")
+        if fast is None:
+            maxd = self.MAX_DETECTIONS
+            detections_list = [np.asarray(d) for d in detections_list]
+            if any(len(d) > maxd for d in detections_list):
+                self._warn(f"more than MAX_DETECTIONS={maxd} detections in a camera: the first {maxd} are used")
+                detections_list = [d[:maxd] for d in detections_list]
+            lst = [d for d in detections_list if len(d)]
+            st.counts[:] = [len(d) for d in detections_list]
+            n = sum(len(d) for d in lst)
+            if n:
+                np.concatenate(lst, axis=0, out=st.packed[:n], casting="same_kind")
+                if self.STRICT_FLOAT32 and not np.array_equal(st.packed[:n], np.concatenate(lst, axis=0)):
+                    raise ValueError("detections are not float32-representable; the device path would round them "
+                                     "(set IterativeTracker.STRICT_FLOAT32 = False to accept the rounding)")
+            st.step(int(frame_id))
         if st.status[0] and not self._warned:
             self._warn("a frame needed more track slots / hypotheses / detections than configured "
                        f"(MAX_TRACKS={self.MAX_TRACKS}, MAX_DETECTIONS={self.MAX_DETECTIONS}); the excess was dropped")
-        tm, cs = st.timing, self._cycle_s
-        return tm[0] * cs, tm[1] * cs, tm[2] * cs
+        t_asso, t_update, t_init = st.timing[:3].tolist()
+        cs = self._cycle_s
+        return t_asso * cs, t_update * cs, t_init * cs
+
+    # results of the latest frame, read from the mapped slot on demand (valid until the next tracking() call)
+    @property
+    def last_ids(self):
+        return self._stream.ids[:int(self._stream.count[0])].copy()
+
+    @property
+    def last_joints(self):
+        return self._stream.joints[:int(self._stream.count[0])].astype(np.float64)
+
+    @property
+    def last_nviews(self):
+        return self._stream.nviews[:int(self._stream.count[0])].copy()
 
     def _warn(self, msg):
         if not self._warned:
@@ -150,7 +186,8 @@ class IterativeTracker(object):
         """Leftover detections per camera, as the reference leaves them after ``init_target_GD``
         (src/tracking/IterativeTracker.py:56-61, 163-167); built on first access after a frame."""
         if self._pending is not None:
-            frame_id, camera_list, boxes_list, detections_list, assoc = self._pending
+            frame_id, camera_list, boxes_list, detections_list = self._pending
+            assoc = self._stream.assoc.copy()
             self._pending = None
             for c, (camera, boxes, dets) in enumerate(zip(camera_list, boxes_list, detections_list)):
                 m = len(dets)

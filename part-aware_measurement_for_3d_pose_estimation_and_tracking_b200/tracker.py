@@ -227,9 +227,11 @@ class SequenceTracker:
 
 
 class FrameStream:
-    """numpy views over the pinned, device-mapped slot of the resident kernel: write ``dets (V,D,J,3)`` /
-    ``counts (V,)``, call ``step(frame_id)``, read ``count[0]``, ``ids``, ``joints``, ``nviews``, ``assoc``,
-    ``timing`` (SM cycles: association, update, initialisation, total)."""
+    """numpy views over the pinned, device-mapped slot of the resident kernel.  Write the frame's detections PACKED
+    (cameras back to back) into ``packed (V*D, J, 3)`` -- ``set_frame()`` does it from the reference's per-camera
+    list -- and the per-camera ``counts (V,)``, call ``step(frame_id)`` (or ``submit`` / ``wait``), then read
+    ``count[0]``, ``ids``, ``joints``, ``nviews``, ``assoc``, ``timing`` (SM cycles: association, update,
+    initialisation, total)."""
 
     def __init__(self, trk: "SequenceTracker"):
         self.trk = trk
@@ -237,29 +239,53 @@ class FrameStream:
         _check(trk.lib, trk.handle, trk.lib.pam_stream_buffers(trk.handle, C.byref(v)))
         c = trk.cfg
         V, D, J, MT = c.num_cameras, c.max_detections, c.num_joints, c.max_tracks
+        self.V, self.D = V, D
 
         def view(ptr, ctype, shape):
             return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=shape)
 
-        self.dets = view(v.dets, C.c_float, (V, D, J, 3))
+        self.packed = view(v.dets, C.c_float, (V * D, J, 3))
         self.counts = view(v.counts, C.c_int32, (V,))
         self.count = view(v.out_count, C.c_int32, (1,))
         self.ids = view(v.out_ids, C.c_int32, (MT,))
         self.joints = view(v.out_joints, C.c_float, (MT, J, 3))
         self.nviews = view(v.out_nviews, C.c_uint8, (MT, J))
         self.assoc = view(v.out_assoc, C.c_int32, (V, D))
-        self.timing = view(v.out_timing, C.c_int32, (4,))
+        self.timing = view(v.out_timing, C.c_int32, (8,))   # [4:7]: protocol timing of the resident kernel
         self.status = view(v.out_status, C.c_int32, (1,))
-        self._step = trk.lib.pam_stream_step
-        self._handle = trk.handle
+        self._lib, self._handle = trk.lib, trk.handle
+        self._submit, self._wait = trk.lib.pam_stream_submit, trk.lib.pam_stream_wait
+
+    def set_frame(self, detections_list):
+        """Per camera ``(m, J, 3)`` arrays (any float dtype) -> the slot.  Returns the number of rows written."""
+        D = self.D
+        lst = [d[:D] for d in detections_list if len(d)]          # at most D detections per camera reach the device
+        self.counts[:] = [min(len(d), D) for d in detections_list]
+        n = sum(len(d) for d in lst)
+        if n:
+            np.concatenate(lst, axis=0, out=self.packed[:n], casting="same_kind")
+        return n
+
+    def set_padded(self, dets, counts):
+        """``dets (V, D, J, 3)`` zero padded + ``counts (V,)`` (one frame of the batched layout) -> the slot."""
+        self.set_frame([dets[c, :counts[c]] for c in range(self.V)])
+
+    def submit(self, frame_id: int):
+        rc = self._submit(self._handle, frame_id)
+        if rc != 0:
+            _check(self._lib, self._handle, rc)
+
+    def wait(self):
+        rc = self._wait(self._handle)
+        if rc != 0:
+            _check(self._lib, self._handle, rc)
 
     def step(self, frame_id: int):
-        rc = self._step(self._handle, frame_id)
-        if rc != 0:
-            _check(self.trk.lib, self.trk.handle, rc)
+        self.submit(frame_id)
+        self.wait()
 
     def close(self):
-        _check(self.trk.lib, self.trk.handle, self.trk.lib.pam_stream_close(self.trk.handle))
+        _check(self._lib, self._handle, self._lib.pam_stream_close(self._handle))
 
 
 def parse_state(blob: np.ndarray, S: int, L, cfg):

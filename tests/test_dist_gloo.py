@@ -45,8 +45,12 @@ def _worker(rank, world, port, q):
     pdist.barrier()
     pdist.reduce_counters(counters)
     g = pdist.gather_results(dict(count=counts, ids=ids), dst=0)
+    # the all-gather bench.py times for BASELINE config 5 (every rank receives every rank's blocks)
+    ag = {k: torch.empty((w,) + tuple(v.shape), dtype=v.dtype) for k, v in dict(count=counts, ids=ids).items()}
+    pdist.all_gather_results(dict(count=counts, ids=ids), ag)
     mx = pdist.max_over_ranks(float(rank + 1))
-    q.put((rank, mine, counters.tolist(), mx, None if g is None else {k: v.numpy() for k, v in g.items()}))
+    q.put((rank, mine, counters.tolist(), mx, None if g is None else {k: v.numpy() for k, v in g.items()},
+           {k: v.numpy() for k, v in ag.items()}))
 
 
 def test_two_rank_shard_reduce_gather():
@@ -61,7 +65,9 @@ def test_two_rank_shard_reduce_gather():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, m0, c0, mx0, g0), (r1, m1, c1, mx1, g1) = res
+    (r0, m0, c0, mx0, g0, a0), (r1, m1, c1, mx1, g1, a1) = res
+    for k in ("count", "ids"):                                  # all-gather: identical on both ranks, equal to the gather
+        assert np.array_equal(a0[k], a1[k]) and np.array_equal(a0[k], g0[k])
     assert m0 == [0, 2, 4] and m1 == [1, 3]                   # round-robin, disjoint, complete
     assert c0 == c1 and c0[1] == 5 * 25                        # all-reduced counters agree on every rank
     assert mx0 == mx1 == 2.0
