@@ -59,7 +59,9 @@ typedef struct pam_config {
     int32_t min_valid_joints;   /* the "> 10" of :145                                              */
     int32_t stale_window;       /* the "<= 3" of :317                                              */
     uint32_t arm_joint_mask;    /* bit j set: joint j is smoothed with arm_sigma (":382" [9,10])   */
-    uint32_t reserved0;
+    uint32_t max_report;        /* rows per frame of the output tensors (ids, joints, nviews, vlist); 0 = max_tracks.
+                                   A frame that reports more tracks keeps the first max_report rows; d_out_count still
+                                   holds the true number, so truncation is detectable.  Smaller rows = less D2H traffic */
     double conf_threshold;      /* CONF_THRESHOLD  :59                                             */
     double epi_threshold;       /* EPI_THRESHOLD   tracking/hypothesis.py:63                       */
     double init_threshold;      /* INIT_THRESHOLD  tracking/hypothesis.py:32                       */
@@ -87,7 +89,8 @@ typedef struct pam_state_layout {
     int64_t off_nviews;         /* uint8  [slot][J]               views used for the last pose      */
     int64_t off_margin;         /* double [n_margins]  decision margins (PAM_MARGIN builds only)    */
     int32_t meta_ints;          /* ints per slot: id,hits,age,tsu,state,already,nviews,hist_start,
-                                   hist_len, view_cid[8], view_time[8], hist_time[hist_ring],
+                                   hist_len, vt_last (usable views of the last update), view_cid[8],
+                                   view_time[8], hist_time[hist_ring],
                                    then 8 bytes camera -> view-slot map and 8 bytes
                                    detection index of each view inside its own frame             */
     int32_t hist_ring;          /* ring length                                                      */
@@ -126,16 +129,21 @@ int pam_track_reset(pam_handle* h, void* d_state, int32_t S, void* stream);
  *   d_dets   [S][T][V][D][J][3] f32 (v,u,conf), zero padded        d_counts [S][T][V] i32
  *   d_out_count [S][T] i32   number of reported tracks (Confirmed and updated this frame,
  *                            ivclabpose.py:265-267), in track-list order
- *   d_out_ids   [S][T][max_tracks] i32          d_out_joints [S][T][max_tracks][J][3] f32
- *   d_out_nviews [S][T][max_tracks][J] u8 (may be NULL)  views each joint was built from
+ *   d_out_ids   [S][T][R] i32          d_out_joints [S][T][R][J][3] f32      (R = max_report, default max_tracks)
+ *   d_out_nviews [S][T][R][J] u8 (may be NULL)  views each joint was built from
  *   d_out_assoc  [S][T][V][D] i32 (may be NULL) track id matched to each detection, -1 = none
  *   d_out_timing [S][T][4] i32 (may be NULL) SM cycles of the frame: association (affinity + assignment),
  *                update, initialisation, total -- the (asso_time, update_time, init_time) tuple
- *                tracking() returns (tracking/IterativeTracker.py:131,169-180); pam_sm_clock_khz converts */
+ *                tracking() returns (tracking/IterativeTracker.py:131,169-180); pam_sm_clock_khz converts
+ *   d_out_vlist [S][T][R][PAM_VLIST_BYTES] u8 (may be NULL) per reported track: [0] usable views of this
+ *                update (= length of its joints_views list, IterativeTracker.py:350), [1] length of the track's view
+ *                list (= len(poses2d), ivclabpose.py:276), [2 ...] camera of every view-list entry in dict-insertion
+ *                order, bit 7 set when that view was matched THIS frame (ivclabpose.py:277-283) */
+#define PAM_VLIST_BYTES 10
 int pam_track_sequences(pam_handle* h, void* d_state, int32_t S, int32_t T, int32_t frame0,
                         const float* d_dets, const int32_t* d_counts, int32_t* d_out_count,
                         int32_t* d_out_ids, float* d_out_joints, uint8_t* d_out_nviews,
-                        int32_t* d_out_assoc, int32_t* d_out_timing, void* stream);
+                        int32_t* d_out_assoc, int32_t* d_out_timing, uint8_t* d_out_vlist, void* stream);
 
 /* Per-sequence status words; synchronises `stream`.  h_status[s] (may be NULL) = hard error code
  * (0 = ok) | PAM_WARN_* bits << 8.  The reference has no capacity limits; here a frame that needs more
@@ -168,7 +176,7 @@ int pam_sm_clock_khz(pam_handle* h, int32_t* khz);
 int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0, int32_t fresh,
                              const float* h_dets, const int32_t* h_counts, int32_t* h_out_count,
                              int32_t* h_out_ids, float* h_out_joints, uint8_t* h_out_nviews,
-                             int32_t* h_out_assoc, int32_t* h_out_timing);
+                             int32_t* h_out_assoc, int32_t* h_out_timing, uint8_t* h_out_vlist);
 
 /* pam_track_status for the internal state of the _host path. */
 int pam_track_host_status(pam_handle* h, int32_t S, int32_t* h_status);
@@ -192,6 +200,7 @@ typedef struct pam_stream_views {
     int32_t* out_assoc;     /* [V][D]                      */
     int32_t* out_timing;    /* [4] SM cycles: association, update, initialisation, total */
     int32_t* out_status;    /* [1] hard error code | PAM_WARN bits << 8 */
+    uint8_t* out_vlist;     /* [max_tracks][PAM_VLIST_BYTES] */
 } pam_stream_views;
 int pam_stream_open(pam_handle* h, int32_t fresh);
 int pam_stream_buffers(pam_handle* h, pam_stream_views* out);

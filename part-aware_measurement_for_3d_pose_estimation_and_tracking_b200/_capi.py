@@ -16,7 +16,7 @@ class PamConfig(C.Structure):
         ("num_cameras", C.c_int32), ("num_joints", C.c_int32), ("max_detections", C.c_int32),
         ("max_tracks", C.c_int32), ("n_init", C.c_int32), ("max_age", C.c_int32),
         ("min_valid_joints", C.c_int32), ("stale_window", C.c_int32),
-        ("arm_joint_mask", C.c_uint32), ("reserved0", C.c_uint32),
+        ("arm_joint_mask", C.c_uint32), ("max_report", C.c_uint32),
         ("conf_threshold", C.c_double), ("epi_threshold", C.c_double), ("init_threshold", C.c_double),
         ("joint_threshold", C.c_double), ("alpha2d", C.c_double), ("lambda_a", C.c_double),
         ("lambda_t", C.c_double), ("sigma", C.c_double), ("arm_sigma", C.c_double),
@@ -35,11 +35,11 @@ class PamStateLayout(C.Structure):
 
 class PamStreamViews(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("dets", "counts", "out_count", "out_ids", "out_joints", "out_nviews",
-                                          "out_assoc", "out_timing", "out_status")]
+                                          "out_assoc", "out_timing", "out_status", "out_vlist")]
 
 
 def make_config(params, num_cameras, max_detections, max_tracks, arm_joints=(9, 10), min_valid_joints=10,
-                stale_window=3, veto_believe=0.5) -> PamConfig:
+                stale_window=3, veto_believe=0.5, max_report=0) -> PamConfig:
     """``params``: mapping / attribute object with the ``iter_args`` fields of
     src/ivclabpose.py:140-156 (``conf_threshold, epi_threshold, init_threshold, joint_threshold,
     num_joints, n_init, max_age, alpha2d, lambda_a, lambda_t, sigma, arm_sigma``)."""
@@ -51,7 +51,7 @@ def make_config(params, num_cameras, max_detections, max_tracks, arm_joints=(9, 
     return PamConfig(
         num_cameras=num_cameras, num_joints=g("num_joints"), max_detections=max_detections,
         max_tracks=max_tracks, n_init=g("n_init"), max_age=g("max_age"),
-        min_valid_joints=min_valid_joints, stale_window=stale_window, arm_joint_mask=mask, reserved0=0,
+        min_valid_joints=min_valid_joints, stale_window=stale_window, arm_joint_mask=mask, max_report=max_report,
         conf_threshold=g("conf_threshold"), epi_threshold=g("epi_threshold"),
         init_threshold=g("init_threshold"), joint_threshold=g("joint_threshold"), alpha2d=g("alpha2d"),
         lambda_a=g("lambda_a"), lambda_t=g("lambda_t"), sigma=g("sigma"), arm_sigma=g("arm_sigma"),
@@ -71,12 +71,12 @@ _PROTOTYPES = [
     ("pam_set_cameras", C.c_int, [_P, _P, _P, _P, _P]),
     ("pam_get_state_layout", C.c_int, [_P, C.POINTER(PamStateLayout)]),
     ("pam_track_reset", C.c_int, [_P, _P, C.c_int32, _P]),
-    ("pam_track_sequences", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("pam_track_sequences", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("pam_track_status", C.c_int, [_P, _P, C.c_int32, _P, _P]),
     ("pam_track_margins", C.c_int, [_P, _P, C.c_int32, _P, _P]),
     ("pam_track_launch_info", C.c_int, [_P, C.c_int32, _P]),
     ("pam_sm_clock_khz", C.c_int, [_P, _P]),
-    ("pam_track_sequences_host", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("pam_track_sequences_host", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("pam_track_host_status", C.c_int, [_P, C.c_int32, _P]),
     ("pam_track_state_to_host", C.c_int, [_P, C.c_int32, _P]),
     ("pam_stream_open", C.c_int, [_P, C.c_int32]),

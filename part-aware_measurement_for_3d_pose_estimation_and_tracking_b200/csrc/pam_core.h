@@ -54,6 +54,7 @@
 #define PAM_HIST 12        // smoothed-pose history ring (max_age + 2 <= PAM_HIST)
 #define PAM_MAX_RADIUS 8   // Gaussian radius int(4 sigma + 0.5)
 #define PAM_MAX_AGEW 8     // stale-view window + 1
+#define PAM_VLIST (2 + PAM_MAX_V)   // bytes per reported track of the optional view-list output
 
 namespace pam {
 

@@ -23,6 +23,7 @@ inline int make_devcfg(const pam_config& p, DevCfg& c, std::string& err, int nbu
     if (!(p.sigma > 0.0) || !(p.arm_sigma > 0.0)) return bad("sigma / arm_sigma must be positive");
     c = DevCfg();
     c.V = p.num_cameras; c.J = p.num_joints; c.D = p.max_detections; c.max_trk = p.max_tracks;
+    c.max_rep = (p.max_report == 0 || (int)p.max_report > p.max_tracks) ? p.max_tracks : (int)p.max_report;
     c.max_hyp = p.num_cameras * p.max_detections < PAM_MAX_HYP ? p.num_cameras * p.max_detections : PAM_MAX_HYP;
     c.n_init = p.n_init; c.max_age = p.max_age; c.min_valid = p.min_valid_joints; c.stale_window = p.stale_window;
     c.arm_mask = p.arm_joint_mask;
@@ -41,6 +42,13 @@ inline int make_devcfg(const pam_config& p, DevCfg& c, std::string& err, int nbu
     c.alpha2d = p.alpha2d; c.lambda_a = p.lambda_a; c.veto_believe = p.veto_believe;
     c.fail_limit = (double)p.num_joints / 3.0;
     c.init_thr_f32 = (float)p.init_threshold;
+    // two-pass affinity: probe J - min_valid joints (at least 3): a pair without enough hits by then is hopeless
+    c.aff_probe = 0;
+    if (c.J >= 8 && c.min_valid >= 0 && c.min_valid < c.J) {
+        int ja = c.J - c.min_valid;
+        if (ja < 3) ja = 3;
+        if (ja <= c.J - 2) c.aff_probe = ja;
+    }
     state_layout(c);
     if (tracker_capable(p)) arena_layout(c, nbuf, raw_in_arena);
     return PAM_OK;

@@ -24,6 +24,7 @@ using namespace pam;
 template <int G, int AFF_UNROLL>
 struct GroupCtx {
     static constexpr int kAffinityUnroll = AFF_UNROLL;
+    static constexpr bool kTwoPassAffinity = (G == 1);      // throughput launches only: it adds a barrier to the frame
     int t;        // thread index inside the group
     int bar;      // named barrier of the group (1..15), unused for one-warp groups
     __device__ __forceinline__ int tid() const { return t; }
@@ -40,6 +41,7 @@ struct GroupCtx {
         else sync();
     }
     __device__ __forceinline__ void atomic_inc(int* p) const { atomicAdd(p, 1); }
+    __device__ __forceinline__ int atomic_inc_ret(int* p) const { return atomicAdd(p, 1); }
     __device__ __forceinline__ long long clock() const { return clock64(); }
 };
 
@@ -97,6 +99,7 @@ struct TrackIO {
     unsigned char* out_nv;  // [S][T][MT][J]
     int* out_assoc;         // [S][T][V][D]
     int* out_timing;        // [S][T][4]
+    unsigned char* out_vlist;  // [S][T][MT][PAM_VLIST]
     int seq_frames;         // frames between consecutive sequences in every tensor above (>= T)
     int* out_status;        // [S] final status word of each sequence, or null
 };
@@ -161,13 +164,14 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
     {
         const int64_t f0 = (int64_t)s * io.seq_frames;
         o.count = io.out_count ? io.out_count + f0 : nullptr;
-        o.ids = io.out_ids ? io.out_ids + f0 * c.max_trk : nullptr;
-        o.joints = io.out_joints ? io.out_joints + f0 * c.max_trk * c.J * 3 : nullptr;
-        o.nviews = io.out_nv ? io.out_nv + f0 * c.max_trk * c.J : nullptr;
+        o.ids = io.out_ids ? io.out_ids + f0 * c.max_rep : nullptr;
+        o.joints = io.out_joints ? io.out_joints + f0 * c.max_rep * c.J * 3 : nullptr;
+        o.nviews = io.out_nv ? io.out_nv + f0 * c.max_rep * c.J : nullptr;
         o.assoc = io.out_assoc ? io.out_assoc + f0 * c.V * c.D : nullptr;
         o.timing = io.out_timing ? io.out_timing + f0 * 4 : nullptr;
+        o.vlist = io.out_vlist ? io.out_vlist + f0 * c.max_rep * PAM_VLIST : nullptr;
     }
-    const int st_ids = c.max_trk, st_joints = c.max_trk * c.J * 3, st_nv = c.max_trk * c.J, st_assoc = c.V * c.D;
+    const int st_ids = c.max_rep, st_joints = c.max_rep * c.J * 3, st_nv = c.max_rep * c.J, st_assoc = c.V * c.D;
     StageHook hook{-1, ctx.tid(), NT, dbuf, cbuf, gd, gc, nfl, c.V, &sh.mbar[0], bulk};
     // convoy: the sequences of a CTA start every frame together, so their warps walk the same code at about the
     // same time and share instruction fetches (24 independent warps otherwise thrash the instruction caches)
@@ -188,6 +192,7 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
         if (o.nviews) o.nviews += st_nv;
         if (o.assoc) o.assoc += st_assoc;
         if (o.timing) o.timing += 4;
+        if (o.vlist) o.vlist += st_ids * PAM_VLIST;
         // two buffers: buffer (t+1)&1 is used for the ((t+1)>>1)-th time; one buffer: for the (t+1)-th time --
         // that is the parity of its barrier phase
         if (more) stage_wait(&sh.mbar[nxt], (unsigned)((nbuf == 2 ? ((t + 1) >> 1) : (t + 1)) & 1), bulk);
@@ -218,7 +223,7 @@ k_track_sequences(const DevCfg c, const CamConst cc, char* __restrict__ state, i
 // ----------------------------------------------------------------------------------------------
 enum { STREAM_CMD_IDLE = 0, STREAM_CMD_EXIT = -1 };
 struct StreamSlot {                      // offsets (bytes) into the mapped slot, computed by the host
-    int o_cmd, o_frame, o_counts, o_dets, o_done, o_count, o_ids, o_joints, o_nv, o_assoc, o_timing, o_status, bytes;
+    int o_cmd, o_frame, o_counts, o_dets, o_done, o_count, o_ids, o_joints, o_nv, o_assoc, o_timing, o_status, o_vlist, bytes;
 };
 
 template <class K, int G>
@@ -245,6 +250,7 @@ k_track_stream(const DevCfg c, const CamConst cc, char* __restrict__ state, char
     FrameOut o;
     o.count = (int*)(slot + so.o_count); o.ids = (int*)(slot + so.o_ids); o.joints = (float*)(slot + so.o_joints);
     o.nviews = (unsigned char*)(slot + so.o_nv); o.assoc = (int*)(slot + so.o_assoc); o.timing = (int*)(slot + so.o_timing);
+    o.vlist = (unsigned char*)(slot + so.o_vlist);
     NoHook hook;
     int last_seq = 0;
     ctx.sync();
@@ -371,7 +377,7 @@ struct pam_handle {
     DevBuf cam;              // packed camera constants
     CamConst cc{};
     // workspace of the *_host entry points
-    DevBuf ws_state, ws_dets, ws_counts, ws_count, ws_ids, ws_joints, ws_nv, ws_assoc, ws_timing;
+    DevBuf ws_state, ws_dets, ws_counts, ws_count, ws_ids, ws_joints, ws_nv, ws_assoc, ws_timing, ws_vlist;
     int ws_S = 0;
     cudaStream_t ws_stream = nullptr, ws_in = nullptr, ws_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_k;
@@ -478,7 +484,7 @@ int pam_destroy(pam_handle* h) {
     if (h->st_stream) cudaStreamDestroy(h->st_stream);
     h->cam.release();
     h->ws_state.release(); h->ws_dets.release(); h->ws_counts.release(); h->ws_count.release();
-    h->ws_ids.release(); h->ws_joints.release(); h->ws_nv.release(); h->ws_assoc.release(); h->ws_timing.release();
+    h->ws_ids.release(); h->ws_joints.release(); h->ws_nv.release(); h->ws_assoc.release(); h->ws_timing.release(); h->ws_vlist.release();
     if (h->ws_stream) cudaStreamDestroy(h->ws_stream);
     if (h->ws_in) cudaStreamDestroy(h->ws_in);
     if (h->ws_out) cudaStreamDestroy(h->ws_out);
@@ -662,13 +668,15 @@ int pam_sm_clock_khz(pam_handle* h, int32_t* khz) {
 
 int pam_track_sequences(pam_handle* h, void* d_state, int32_t S, int32_t T, int32_t frame0, const float* d_dets,
                         const int32_t* d_counts, int32_t* d_out_count, int32_t* d_out_ids, float* d_out_joints,
-                        uint8_t* d_out_nviews, int32_t* d_out_assoc, int32_t* d_out_timing, void* stream) {
+                        uint8_t* d_out_nviews, int32_t* d_out_assoc, int32_t* d_out_timing, uint8_t* d_out_vlist,
+                        void* stream) {
     if (!h || !d_state || !d_dets || !d_counts || S < 0 || T < 0) return fail(h, PAM_E_INVALID, "bad argument");
     if (!h->have_cameras) return fail(h, PAM_E_NOCAMERAS, "pam_set_cameras has not been called");
     if (!tracker_capable(h->cfg)) return fail(h, PAM_E_INVALID, "the stateful tracker handles at most 8 cameras");
     if (S == 0 || T == 0) return PAM_OK;
     CK(cudaSetDevice(h->device));
-    TrackIO io{d_dets, d_counts, d_out_count, d_out_ids, d_out_joints, d_out_nviews, d_out_assoc, d_out_timing, T, nullptr};
+    TrackIO io{d_dets, d_counts, d_out_count, d_out_ids, d_out_joints, d_out_nviews, d_out_assoc, d_out_timing, d_out_vlist,
+               T, nullptr};
     return launch_track(h, d_state, S, T, frame0, io, (cudaStream_t)stream);
 }
 
@@ -733,7 +741,7 @@ int pam_track_margins(pam_handle* h, const void* d_state, int32_t S, double* h_m
 
 int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0, int32_t fresh, const float* h_dets,
                              const int32_t* h_counts, int32_t* h_out_count, int32_t* h_out_ids, float* h_out_joints,
-                             uint8_t* h_out_nviews, int32_t* h_out_assoc, int32_t* h_out_timing) {
+                             uint8_t* h_out_nviews, int32_t* h_out_assoc, int32_t* h_out_timing, uint8_t* h_out_vlist) {
     if (!h || !h_dets || !h_counts || !h_out_count || S <= 0 || T <= 0) return fail(h, PAM_E_INVALID, "bad argument");
     if (!h->have_cameras) return fail(h, PAM_E_NOCAMERAS, "pam_set_cameras has not been called");
     if (!tracker_capable(h->cfg)) return fail(h, PAM_E_INVALID, "the stateful tracker handles at most 8 cameras");
@@ -744,8 +752,8 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
     const DevCfg& c = h->dc;
     const size_t ST = (size_t)S * T;
     const size_t b_dets = ST * c.V * c.D * c.J * 3 * 4, b_counts = ST * c.V * 4, b_count = ST * 4;
-    const size_t b_ids = ST * c.max_trk * 4, b_joints = ST * c.max_trk * c.J * 3 * 4, b_nv = ST * c.max_trk * c.J;
-    const size_t b_assoc = ST * c.V * c.D * 4, b_timing = ST * 16;
+    const size_t b_ids = ST * c.max_rep * 4, b_joints = ST * c.max_rep * c.J * 3 * 4, b_nv = ST * c.max_rep * c.J;
+    const size_t b_assoc = ST * c.V * c.D * 4, b_timing = ST * 16, b_vlist = ST * c.max_rep * PAM_VLIST;
     if (fresh || S != h->ws_S) {
         CK(h->ws_state.reserve((size_t)c.seq_bytes * S));
         CK(cudaMemsetAsync(h->ws_state.p, 0, (size_t)c.seq_bytes * S, st));
@@ -758,7 +766,8 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
         auto up = [](size_t x) { return (x + 255) / 256 * 256; };
         const size_t o_dets = 0, o_counts = o_dets + up(b_dets), o_count = o_counts + up(b_counts);
         const size_t o_ids = o_count + up(b_count), o_joints = o_ids + up(b_ids), o_nv = o_joints + up(b_joints);
-        const size_t o_assoc = o_nv + up(b_nv), o_timing = o_assoc + up(b_assoc), o_status = o_timing + up(b_timing);
+        const size_t o_assoc = o_nv + up(b_nv), o_timing = o_assoc + up(b_assoc), o_vlist = o_timing + up(b_timing);
+        const size_t o_status = o_vlist + up(b_vlist);
         const size_t total = o_status + up((size_t)S * 4);
         if (total <= 256 * 1024) {
             if (total > h->zc_cap) {
@@ -775,7 +784,8 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
             TrackIO io{(const float*)(dz + o_dets), (const int32_t*)(dz + o_counts), (int32_t*)(dz + o_count),
                        h_out_ids ? (int32_t*)(dz + o_ids) : nullptr, h_out_joints ? (float*)(dz + o_joints) : nullptr,
                        h_out_nviews ? (uint8_t*)(dz + o_nv) : nullptr, h_out_assoc ? (int32_t*)(dz + o_assoc) : nullptr,
-                       h_out_timing ? (int32_t*)(dz + o_timing) : nullptr, T, (int*)(dz + o_status)};
+                       h_out_timing ? (int32_t*)(dz + o_timing) : nullptr, h_out_vlist ? (uint8_t*)(dz + o_vlist) : nullptr, T,
+                       (int*)(dz + o_status)};
             // completion is detected by polling the status words the groups write last (a few us sooner
             // than a stream synchronisation wakes up); bounded, then the stream is synchronised anyway
             volatile int32_t* stv = (volatile int32_t*)(z + o_status);
@@ -801,6 +811,7 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
             if (h_out_nviews) memcpy(h_out_nviews, z + o_nv, b_nv);
             if (h_out_assoc) memcpy(h_out_assoc, z + o_assoc, b_assoc);
             if (h_out_timing) memcpy(h_out_timing, z + o_timing, b_timing);
+            if (h_out_vlist) memcpy(h_out_vlist, z + o_vlist, b_vlist);
             const int32_t* stw = (const int32_t*)(z + o_status);
             for (int s = 0; s < S; ++s)
                 if (stw[s] & 0xff) return status_message(h, stw, S);     // hard errors only; warnings: pam_track_host_status
@@ -815,6 +826,7 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
     if (h_out_nviews) CK(h->ws_nv.reserve(b_nv));
     if (h_out_assoc) CK(h->ws_assoc.reserve(b_assoc));
     if (h_out_timing) CK(h->ws_timing.reserve(b_timing));
+    if (h_out_vlist) CK(h->ws_vlist.reserve(b_vlist));
     // Pipeline over chunks of frames: the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap
     // the kernel of chunk k (three streams; tracker state stays in HBM between the chunk launches).
     if (!h->ws_in) CK(cudaStreamCreateWithFlags(&h->ws_in, cudaStreamNonBlocking));
@@ -844,8 +856,8 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
     CK(cudaEventRecord(h->ev_k[nchunks], st));
     CK(cudaStreamWaitEvent(h->ws_in, h->ev_k[nchunks], 0));
     const size_t f_dets = (size_t)c.V * c.D * c.J * 3 * 4, f_counts = (size_t)c.V * 4, f_count = 4;
-    const size_t f_ids = (size_t)c.max_trk * 4, f_joints = (size_t)c.max_trk * c.J * 3 * 4, f_nv = (size_t)c.max_trk * c.J;
-    const size_t f_assoc = (size_t)c.V * c.D * 4, f_timing = 16;
+    const size_t f_ids = (size_t)c.max_rep * 4, f_joints = (size_t)c.max_rep * c.J * 3 * 4, f_nv = (size_t)c.max_rep * c.J;
+    const size_t f_assoc = (size_t)c.V * c.D * 4, f_timing = 16, f_vlist = (size_t)c.max_rep * PAM_VLIST;
     auto chunk2d = [&](void* dst, const void* src, size_t fbytes, int t0, int n, cudaMemcpyKind kind, cudaStream_t sx) {
         return cudaMemcpy2DAsync((char*)dst + (size_t)t0 * fbytes, (size_t)T * fbytes, (const char*)src + (size_t)t0 * fbytes,
                                  (size_t)T * fbytes, (size_t)n * fbytes, (size_t)S, kind, sx);
@@ -858,11 +870,12 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
         CK(cudaStreamWaitEvent(st, h->ev_in[k], 0));
         TrackIO io{(const float*)h->ws_dets.p + (size_t)t0 * (f_dets / 4), (const int32_t*)h->ws_counts.p + (size_t)t0 * c.V,
                    (int32_t*)h->ws_count.p + t0,
-                   h_out_ids ? (int32_t*)h->ws_ids.p + (size_t)t0 * c.max_trk : nullptr,
+                   h_out_ids ? (int32_t*)h->ws_ids.p + (size_t)t0 * c.max_rep : nullptr,
                    h_out_joints ? (float*)h->ws_joints.p + (size_t)t0 * (f_joints / 4) : nullptr,
                    h_out_nviews ? (uint8_t*)h->ws_nv.p + (size_t)t0 * f_nv : nullptr,
                    h_out_assoc ? (int32_t*)h->ws_assoc.p + (size_t)t0 * (f_assoc / 4) : nullptr,
-                   h_out_timing ? (int32_t*)h->ws_timing.p + (size_t)t0 * 4 : nullptr, T, nullptr};
+                   h_out_timing ? (int32_t*)h->ws_timing.p + (size_t)t0 * 4 : nullptr,
+                   h_out_vlist ? (uint8_t*)h->ws_vlist.p + (size_t)t0 * f_vlist : nullptr, T, nullptr};
         int rc = launch_track(h, h->ws_state.p, S, n, frame0 + t0, io, st);
         if (rc != PAM_OK) return rc;
         CK(cudaEventRecord(h->ev_k[k], st));
@@ -873,6 +886,7 @@ int pam_track_sequences_host(pam_handle* h, int32_t S, int32_t T, int32_t frame0
         if (h_out_nviews) CK(chunk2d(h_out_nviews, h->ws_nv.p, f_nv, t0, n, cudaMemcpyDeviceToHost, h->ws_out));
         if (h_out_assoc) CK(chunk2d(h_out_assoc, h->ws_assoc.p, f_assoc, t0, n, cudaMemcpyDeviceToHost, h->ws_out));
         if (h_out_timing) CK(chunk2d(h_out_timing, h->ws_timing.p, f_timing, t0, n, cudaMemcpyDeviceToHost, h->ws_out));
+        if (h_out_vlist) CK(chunk2d(h_out_vlist, h->ws_vlist.p, f_vlist, t0, n, cudaMemcpyDeviceToHost, h->ws_out));
     }
     CK(cudaStreamSynchronize(h->ws_out));
     drain.armed = false;
@@ -934,9 +948,10 @@ int pam_stream_open(pam_handle* h, int32_t fresh) {
         auto take = [&](size_t bytes) { const int at = o; o += (int)((bytes + 127) / 128 * 128); return at; };
         so.o_cmd = take(16); so.o_frame = so.o_cmd + 4; so.o_counts = take(4 * PAM_MAX_V);
         so.o_dets = take((size_t)c.V * c.D * c.J * 3 * 4);
-        so.o_done = take(4); so.o_count = take(4); so.o_ids = take((size_t)c.max_trk * 4);
-        so.o_joints = take((size_t)c.max_trk * c.J * 3 * 4); so.o_nv = take((size_t)c.max_trk * c.J);
+        so.o_done = take(4); so.o_count = take(4); so.o_ids = take((size_t)c.max_rep * 4);
+        so.o_joints = take((size_t)c.max_rep * c.J * 3 * 4); so.o_nv = take((size_t)c.max_rep * c.J);
         so.o_assoc = take((size_t)c.V * c.D * 4); so.o_timing = take(32); so.o_status = take(4);
+        so.o_vlist = take((size_t)c.max_rep * PAM_VLIST);
         so.bytes = o;
         CK(cudaHostAlloc((void**)&h->st_slot, (size_t)o, cudaHostAllocMapped));
         memset(h->st_slot, 0, (size_t)o);
@@ -954,6 +969,7 @@ int pam_stream_buffers(pam_handle* h, pam_stream_views* v) {
     v->out_joints = (float*)(h->st_slot + so.o_joints); v->out_nviews = (uint8_t*)(h->st_slot + so.o_nv);
     v->out_assoc = (int32_t*)(h->st_slot + so.o_assoc); v->out_timing = (int32_t*)(h->st_slot + so.o_timing);
     v->out_status = (int32_t*)(h->st_slot + so.o_status);
+    v->out_vlist = (uint8_t*)(h->st_slot + so.o_vlist);
     return PAM_OK;
 }
 

@@ -51,6 +51,7 @@ enum {
 // Launch-constant parameters (kernel argument; lives in the constant bank).
 struct DevCfg {
     int V, J, D, max_trk, max_hyp;
+    int max_rep;                             // rows per frame of the output tensors (<= max_trk)
     float inv_J, inv_D, inv_V, inv_VD;       // reciprocals for fast_div
     int n_init, max_age, min_valid, stale_window;
     uint32_t arm_mask;
@@ -67,6 +68,7 @@ struct DevCfg {
     // per-sequence working arena: [SeqShared<K> (compile-time capacity class K)][detection buffers][raw pose]
     int caps;                                // capacity class (CAPS_*), chosen from V, D, J, max_trk
     int convoy;                              // one-warp groups of a CTA start every frame together (instruction-cache locality)
+    int aff_probe;                           // two-pass affinity: joints evaluated before hopeless pairs are dropped (0 = off)
     int nbuf;                                // detection buffers: 2 = next frame staged during the current one
     int frame_floats;                        // V * D * J * 3, padded to a multiple of 4
     int a_dets, a_raw;                       // byte offsets of the run-time sized tail (a_raw < 0: raw pose in HBM scratch)
@@ -84,6 +86,7 @@ struct SeqHeader {
 
 struct TrkMeta {
     int track_id, hits, age, tsu, state, already, nviews, hist_start, hist_len;
+    int vt_last;                        // usable views of the last successful update (length of its joints_views)
     int view_cid[PAM_MAX_V];
     int view_time[PAM_MAX_V];
     int hist_time[PAM_HIST];
@@ -99,6 +102,7 @@ struct FrameScalars {
     int do_init;
     int hyp_n;
     int warned;            // something was dropped this frame
+    int n_surv;            // two-pass affinity: (track, camera, detection) items that survived the probe
 };
 
 // One usable view of a track for the current frame: where its (v, u, conf) triples live (the staged
@@ -169,6 +173,9 @@ struct SeqShared {
     int fail[K::T];                          // joints left with < 2 views
     // t2d [V][T] then d2t [V][D]: reset together, as ints
     signed char match[(K::V * K::T + K::V * K::D + 3) / 4 * 4];
+    // two-pass affinity: items that survived the probe, and their valid-joint count so far
+    unsigned short surv[K::V * K::T * K::D];
+    unsigned char pcnt[K::V][K::T][K::D];
     signed char last[K::T];                  // ring index of the last pose
     signed char gv_n[K::T];
     signed char new_view[K::T];              // a matched camera is not in the track's view list yet
@@ -261,6 +268,9 @@ struct FrameOut {
     unsigned char* nviews; // [max_trk][J]
     int* assoc;            // [V][D]  track id matched to each detection, -1 = unmatched
     int* timing;           // [4]     SM cycles spent in association / update / initialisation / whole frame
+    unsigned char* vlist;  // [max_trk][PAM_VLIST]  per reported track: usable views of this update, length of the track's
+                           //         view list (= len(poses2d)), then the camera of every list entry in dict order,
+                           //         bit 7 set when that view was matched this frame (ivclabpose.py:272-281)
 };
 
 // The working set of one sequence as the code sees it: fixed part, camera constants, run-time tail, global state.
@@ -295,7 +305,9 @@ struct HostCtx {
     inline void sync() const {}
     inline void phase_sync() const {}
     inline void atomic_inc(int* p) const { *p += 1; }
+    inline int atomic_inc_ret(int* p) const { return (*p)++; }
     inline long long clock() const { return 0; }
+    static bool kTwoPassAffinity;            // set by the harness (PAM_HOSTEMU_TWOPASS=1)
 };
 struct NoHook {
     PAM_HD void dets_released() const {}
@@ -597,7 +609,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
         sh.fail[i] = 0;
         sh.new_view[i] = 0;
     }
-    if (ctx.tid() == ctx.nthreads() - 1) { fs.any_conflict = 0; fs.any_deleted = 0; }
+    if (ctx.tid() == ctx.nthreads() - 1) { fs.any_conflict = 0; fs.any_deleted = 0; fs.n_surv = 0; }
     PAM_FOR_REV(cc, V) {
         int mm = counts[cc];
         if (mm > D || mm < 0) { hdr.warn |= WARN_DET_OVERFLOW; fs.warned = 1; mm = (mm < 0) ? 0 : D; }
@@ -611,22 +623,19 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
     ctx.phase_sync();
 
     // ---- phase 2: track x detection affinity (IterativeTracker.py:139-149) ----------------------
-    PAM_FOR(it, V * n * D) {
-        const int i = fast_div(it, c.inv_VD), rem = it - i * (V * D), cam = fast_div(rem, c.inv_D), d = rem - cam * D;
-        if (d >= sh.m[cam]) continue;
-        // reprojection of the track's last pose into this camera (ivclabpose.py:91-98), recomputed per
-        // detection: cheaper than staging V x n x J pixel pairs in shared memory
+    // joints j0..j1-1 of one (track, camera, detection): reprojection of the track's last pose into the camera
+    // (ivclabpose.py:91-98; recomputed per detection: cheaper than staging V x n x J pixel pairs in shared memory),
+    // distance to the detection, c = 1 - d / (alpha2d dt); running sum and count of the joints with c > 0
+    auto affinity_joints = [&](int i, int cam, int d, int j0, int j1, double& sum, int& cnt) {
         const double* X = g.hist + (int64_t)(hdr.order[i] * PAM_HIST + sh.last[i]) * J3;
         const double* P = sq.Pc(cam);
         const double p0 = P[0], p1 = P[1], p2 = P[2], p3 = P[3], p4 = P[4], p5 = P[5], p6 = P[6], p7 = P[7];
         const double p8 = P[8], p9 = P[9], p10 = P[10], p11 = P[11];
         const float* q = dets + (int64_t)(cam * D + d) * J3;
         const double inv_denom = sh.inv_denom[i];
-        double sum = 0.0;
-        int cnt = 0;
         // joints in flight per thread (the chain per joint is ~20 deep): 2 in the register-lean variants,
-        // 4 where the launch shape leaves the full register budget (single streams)
-        PAM_UNROLL_N(Ctx::kAffinityUnroll) for (int j = 0; j < J; ++j) {
+        // 4 where the launch shape leaves the full register budget
+        PAM_UNROLL_N(Ctx::kAffinityUnroll) for (int j = j0; j < j1; ++j) {
             const double x = X[j * 3], y = X[j * 3 + 1], z = X[j * 3 + 2];
             const double iw = rcp_f64(p8 * x + p9 * y + p10 * z + p11);
             const double dv = (p4 * x + p5 * y + p6 * z + p7) * iw - (double)q[j * 3 + 0];
@@ -635,11 +644,50 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
             PAM_NOTE(MG_ASSOC_C, cj);
             if (cj > 0.0) { sum += cj; ++cnt; }
         }
+    };
+    auto affinity_value = [&](int i, double sum, int cnt) {
         double a = (cnt > c.min_valid) ? sum * rcp_f64((double)cnt) : 0.0;
         a = a * sh.inv_decay[i];
         if (a != a) a = 0.0;
         if (a > 0.0) PAM_NOTE(MG_ASSIGN, a);
-        sh.aff[cam][i][d] = a;
+        return a;
+    };
+    if (Ctx::kTwoPassAffinity && c.aff_probe > 0) {
+        // Throughput launches.  Most (track, detection) pairs belong to different people: after the first
+        // `aff_probe` joints such a pair can no longer collect more than min_valid joints with c > 0, so its
+        // affinity is exactly 0 (IterativeTracker.py:145-147) and it is dropped.  The survivors -- about one
+        // per (track, camera) -- are compacted and finished in a second, densely packed pass; their partial
+        // sums continue in the same order, so every affinity is bit-identical to the single-pass value.
+        const int JA = c.aff_probe;
+        PAM_FOR(it, V * n * D) {
+            const int i = fast_div(it, c.inv_VD), rem = it - i * (V * D), cam = fast_div(rem, c.inv_D), d = rem - cam * D;
+            if (d >= sh.m[cam]) continue;
+            double sum = 0.0;
+            int cnt = 0;
+            affinity_joints(i, cam, d, 0, JA, sum, cnt);
+            if (cnt + (J - JA) <= c.min_valid) { sh.aff[cam][i][d] = 0.0; continue; }
+            sh.aff[cam][i][d] = sum;
+            sh.pcnt[cam][i][d] = (unsigned char)cnt;
+            sh.surv[ctx.atomic_inc_ret(&fs.n_surv)] = (unsigned short)it;
+        }
+        ctx.sync();
+        PAM_FOR(k, fs.n_surv) {
+            const int it = sh.surv[k];
+            const int i = fast_div(it, c.inv_VD), rem = it - i * (V * D), cam = fast_div(rem, c.inv_D), d = rem - cam * D;
+            double sum = sh.aff[cam][i][d];
+            int cnt = sh.pcnt[cam][i][d];
+            affinity_joints(i, cam, d, JA, J, sum, cnt);
+            sh.aff[cam][i][d] = affinity_value(i, sum, cnt);
+        }
+    } else {
+        PAM_FOR(it, V * n * D) {
+            const int i = fast_div(it, c.inv_VD), rem = it - i * (V * D), cam = fast_div(rem, c.inv_D), d = rem - cam * D;
+            if (d >= sh.m[cam]) continue;
+            double sum = 0.0;
+            int cnt = 0;
+            affinity_joints(i, cam, d, 0, J, sum, cnt);
+            sh.aff[cam][i][d] = affinity_value(i, sum, cnt);
+        }
     }
     ctx.phase_sync();
 
@@ -905,7 +953,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
         PAM_FOR(it, n * J) {
             const int i = fast_div(it, c.inv_J), j = it - i * J;
             const int k = sh.out_row[i];
-            if (k < 0) continue;
+            if (k < 0 || k >= c.max_rep) continue;       // rows beyond the output stride are dropped (count tells)
             const double* o = rawb + (int64_t)(i * J + j) * 3;
             if (out.joints) {
                 float* oj = out.joints + (int64_t)(k * J + j) * 3;
@@ -931,6 +979,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
             }
             t.hits += 1;
             t.tsu = 0;
+            t.vt_last = sh.gv_n[i];
             if (t.state == ST_TENTATIVE && t.hits >= c.n_init) t.state = ST_CONFIRMED;
             if (t.state == ST_CONFIRMED) flag |= 2;
         } else {
@@ -938,7 +987,14 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
             else if (t.tsu >= c.max_age) t.state = ST_DELETED;
         }
         if (t.state != ST_DELETED) flag |= 1; else fs.any_deleted = 1;
-        if ((flag & 2) && out.ids) out.ids[sh.out_row[i]] = t.track_id;     // reported <=> out_row >= 0
+        if ((flag & 2) && out.ids && sh.out_row[i] < c.max_rep) out.ids[sh.out_row[i]] = t.track_id;     // reported <=> out_row >= 0
+        if ((flag & 2) && out.vlist && sh.out_row[i] < c.max_rep) {
+            unsigned char* vl = out.vlist + sh.out_row[i] * PAM_VLIST;
+            vl[0] = (unsigned char)sh.gv_n[i];
+            vl[1] = (unsigned char)t.nviews;
+            PAM_NOUNROLL for (int k = 0; k < t.nviews; ++k)
+                vl[2 + k] = (unsigned char)(t.view_cid[k] | (t.view_time[k] == frame ? 0x80 : 0));
+        }
         sh.life_flag[i] = (signed char)flag;
     }
     // ... while the thread below them seeds the hypothesis list of the initialisation (if any)
@@ -1049,6 +1105,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
                 t.track_id = hdr.next_id++;
                 t.hits = 1; t.age = 1; t.tsu = 0; t.state = ST_TENTATIVE; t.already = 0;
                 t.nviews = sh.hyp_nviews[h];
+                t.vt_last = t.nviews;
                 PAM_NOUNROLL for (int cc2 = 0; cc2 < PAM_MAX_V; ++cc2) t.view_slot[cc2] = -1;
                 PAM_NOUNROLL for (int k = 0; k < t.nviews; ++k) {
                     const int hc = sh.hyp_cam[h][k];

@@ -10,7 +10,7 @@ import time as _time
 
 import numpy as np
 
-from _pkg import camera as _camera, tracker as _tracker, capi as _capi
+from _pkg import camera as _camera, tracker as _tracker, capi as _capi, results as _results
 from calculate import get_believe
 
 
@@ -30,11 +30,9 @@ class IterTrack:
         self.velocity_3d = d["velocity_3d"]
         self.joints = d["velocity_3d"].shape[0]
         self.poses2d = {cid: {"time": v["time"], "camera": cameras[cid], "pose": v["pose"]} for cid, v in d["poses2d"].items()}
-        nv = d["joint_views"]
-        jv = [[] for _ in range(max(len(cameras), 1))]
-        for j, k in enumerate(nv):
-            if k > 0:
-                jv[int(k) - 1].append(j)
+        # joints_views of the newest pose as get_3dpose / get_3dpose_jf build it: one bucket per usable view of that
+        # update (src/tracking/IterativeTracker.py:350-357); older history entries do not keep theirs on the device
+        jv = _results.joints_views_list(d["joint_views"], d["views_used"])
         self.poses3d = [{"time": p["time"], "pose3d": p["pose3d"], "joints_views": None} for p in d["poses3d"]]
         if self.poses3d:
             self.poses3d[-1]["joints_views"] = jv

@@ -11,3 +11,4 @@ ops = importlib.import_module(pkg.__name__ + ".ops")
 camera = importlib.import_module(pkg.__name__ + ".camera")
 tracker = importlib.import_module(pkg.__name__ + ".tracker")
 capi = importlib.import_module(pkg.__name__ + "._capi")
+results = importlib.import_module(pkg.__name__ + ".results")

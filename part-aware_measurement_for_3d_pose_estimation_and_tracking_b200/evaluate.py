@@ -32,7 +32,7 @@ def pcp_counters(trk, out, gt, gt_valid=None, frame_begin=0, frame_end=None, alp
     st = torch.cuda.current_stream(dev).cuda_stream
     p = lambda t: C.c_void_p(t.data_ptr())
     rc = trk.lib.pam_eval_pcp(trk.handle, p(out["count"]), p(out["joints"]), p(gt), p(gt_valid), S, T, P,
-                              trk.cfg.max_tracks, 1 if J == 17 else 0, frame_begin, T if frame_end is None else frame_end,
+                              trk.out_rows, 1 if J == 17 else 0, frame_begin, T if frame_end is None else frame_end,
                               float(alpha), p(counters), p(mpjpe), C.c_void_p(st))
     _check(trk.lib, trk.handle, rc)
     return counters, mpjpe
@@ -59,7 +59,7 @@ def panoptic_match(trk, out, gt_mm, gt_vis, n_gt):
     import torch
     S, T, G = gt_mm.shape[0], gt_mm.shape[1], gt_mm.shape[2]
     dev = gt_mm.device
-    MT = trk.cfg.max_tracks
+    MT = trk.out_rows
     mp = torch.empty((S, T, MT), dtype=torch.float64, device=dev)
     gi = torch.empty((S, T, MT), dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream(dev).cuda_stream

@@ -14,6 +14,7 @@ import numpy as np
 from . import _capi, camera as _camera
 
 TENTATIVE, CONFIRMED, DELETED = 1, 2, 3
+VLIST_BYTES = 10          # include/pam.h PAM_VLIST_BYTES
 
 
 PAM_E_CAPACITY = -4
@@ -47,9 +48,13 @@ class SequenceTracker:
 
     def __init__(self, cameras: Sequence, params, num_sequences: int = 1, max_detections: int = 8,
                  max_tracks: int = 8, arm_joints: Sequence[int] = (9, 10), min_valid_joints: int = 10,
-                 device: int = 0):
+                 device: int = 0, max_report: int = 0):
+        """``max_report``: rows per frame of the output tensors (0 = ``max_tracks``); a frame that reports more tracks
+        keeps the first ``max_report`` rows, ``count`` still tells the true number."""
         self.lib = _capi.load_library()
-        self.cfg = _capi.make_config(params, len(cameras), max_detections, max_tracks, arm_joints, min_valid_joints)
+        self.cfg = _capi.make_config(params, len(cameras), max_detections, max_tracks, arm_joints, min_valid_joints,
+                                     max_report=max_report)
+        self.out_rows = max_report if 0 < max_report <= max_tracks else max_tracks
         self.S = int(num_sequences)
         self.device = int(device)
         self.handle = C.c_void_p()
@@ -95,21 +100,23 @@ class SequenceTracker:
         self.next_frame = 0
 
     # -- device-pointer path ------------------------------------------------------------------
-    def alloc_outputs(self, T: int, nviews: bool = True, assoc: bool = False, timing: bool = False):
+    def alloc_outputs(self, T: int, nviews: bool = True, assoc: bool = False, timing: bool = False, vlist: bool = False):
         torch = self._torch()
         dev = f"cuda:{self.device}"
         c = self.cfg
         out = dict(count=torch.empty((self.S, T), dtype=torch.int32, device=dev),
-                   ids=torch.empty((self.S, T, c.max_tracks), dtype=torch.int32, device=dev),
-                   joints=torch.empty((self.S, T, c.max_tracks, c.num_joints, 3), dtype=torch.float32, device=dev))
-        out["nviews"] = torch.empty((self.S, T, c.max_tracks, c.num_joints), dtype=torch.uint8, device=dev) if nviews else None
+                   ids=torch.empty((self.S, T, self.out_rows), dtype=torch.int32, device=dev),
+                   joints=torch.empty((self.S, T, self.out_rows, c.num_joints, 3), dtype=torch.float32, device=dev))
+        out["nviews"] = torch.empty((self.S, T, self.out_rows, c.num_joints), dtype=torch.uint8, device=dev) if nviews else None
         out["assoc"] = torch.empty((self.S, T, c.num_cameras, c.max_detections), dtype=torch.int32, device=dev) if assoc else None
         if timing:
             out["timing"] = torch.zeros((self.S, T, 4), dtype=torch.int32, device=dev)
+        if vlist:
+            out["vlist"] = torch.zeros((self.S, T, self.out_rows, VLIST_BYTES), dtype=torch.uint8, device=dev)
         return out
 
     def run(self, dets, counts, out: Optional[dict] = None, frame0: Optional[int] = None, nviews=True, assoc=False,
-            timing=False):
+            timing=False, vlist=False):
         """``dets`` (S,T,V,D,J,3) float32 and ``counts`` (S,T,V) int32 CUDA tensors.  Asynchronous on
         torch's current stream; returns the dict of output tensors."""
         torch = self._torch()
@@ -121,13 +128,13 @@ class SequenceTracker:
         if self._state is None:
             self.restart()
         if out is None:
-            out = self.alloc_outputs(T, nviews, assoc, timing)
+            out = self.alloc_outputs(T, nviews, assoc, timing, vlist)
         f0 = self.next_frame if frame0 is None else frame0
         st = torch.cuda.current_stream(self.device).cuda_stream
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         rc = self.lib.pam_track_sequences(self.handle, p(self._state), S, T, f0, p(dets), p(counts), p(out["count"]),
                                           p(out["ids"]), p(out["joints"]), p(out.get("nviews")), p(out.get("assoc")),
-                                          p(out.get("timing")), C.c_void_p(st))
+                                          p(out.get("timing")), p(out.get("vlist")), C.c_void_p(st))
         _check(self.lib, self.handle, rc)
         self.next_frame = f0 + T
         return out
@@ -175,7 +182,8 @@ class SequenceTracker:
 
     # -- host-buffer path (what a reference-side caller would use) ------------------------------
     def run_host(self, dets: np.ndarray, counts: np.ndarray, frame0: Optional[int] = None, fresh: bool = False,
-                 nviews: bool = True, assoc: bool = False, out: Optional[dict] = None, timing: bool = False):
+                 nviews: bool = True, assoc: bool = False, out: Optional[dict] = None, timing: bool = False,
+                 vlist: bool = False):
         """numpy in, numpy out through ``pam_track_sequences_host`` (H2D + kernel + D2H + sync)."""
         c = self.cfg
         dets = np.ascontiguousarray(dets, np.float32)
@@ -183,17 +191,20 @@ class SequenceTracker:
         S, T = dets.shape[0], dets.shape[1]
         assert tuple(dets.shape[2:]) == (c.num_cameras, c.max_detections, c.num_joints, 3), dets.shape
         if out is None:
-            out = dict(count=np.empty((S, T), np.int32), ids=np.empty((S, T, c.max_tracks), np.int32),
-                       joints=np.empty((S, T, c.max_tracks, c.num_joints, 3), np.float32),
-                       nviews=np.empty((S, T, c.max_tracks, c.num_joints), np.uint8) if nviews else None,
+            R = self.out_rows
+            out = dict(count=np.empty((S, T), np.int32), ids=np.empty((S, T, R), np.int32),
+                       joints=np.empty((S, T, R, c.num_joints, 3), np.float32),
+                       nviews=np.empty((S, T, R, c.num_joints), np.uint8) if nviews else None,
                        assoc=np.empty((S, T, c.num_cameras, c.max_detections), np.int32) if assoc else None,
-                       timing=np.zeros((S, T, 4), np.int32) if timing else None)
+                       timing=np.zeros((S, T, 4), np.int32) if timing else None,
+                       vlist=np.zeros((S, T, R, VLIST_BYTES), np.uint8) if vlist else None)
         if fresh:
             self.next_frame = 0
         f0 = self.next_frame if frame0 is None else frame0
         rc = self.lib.pam_track_sequences_host(self.handle, S, T, f0, 1 if fresh else 0, _np_ptr(dets), _np_ptr(counts),
                                                _np_ptr(out["count"]), _np_ptr(out["ids"]), _np_ptr(out["joints"]),
-                                               _np_ptr(out.get("nviews")), _np_ptr(out.get("assoc")), _np_ptr(out.get("timing")))
+                                               _np_ptr(out.get("nviews")), _np_ptr(out.get("assoc")), _np_ptr(out.get("timing")),
+                                               _np_ptr(out.get("vlist")))
         _check(self.lib, self.handle, rc)
         self.next_frame = f0 + T
         self._host_S = S
@@ -238,7 +249,7 @@ class FrameStream:
         v = _capi.PamStreamViews()
         _check(trk.lib, trk.handle, trk.lib.pam_stream_buffers(trk.handle, C.byref(v)))
         c = trk.cfg
-        V, D, J, MT = c.num_cameras, c.max_detections, c.num_joints, c.max_tracks
+        V, D, J, MT = c.num_cameras, c.max_detections, c.num_joints, trk.out_rows
         self.V, self.D = V, D
 
         def view(ptr, ctype, shape):
@@ -253,6 +264,7 @@ class FrameStream:
         self.assoc = view(v.out_assoc, C.c_int32, (V, D))
         self.timing = view(v.out_timing, C.c_int32, (8,))   # [4:7]: protocol timing of the resident kernel
         self.status = view(v.out_status, C.c_int32, (1,))
+        self.vlist = view(v.out_vlist, C.c_uint8, (MT, VLIST_BYTES))
         self._lib, self._handle = trk.lib, trk.handle
         self._submit, self._wait = trk.lib.pam_stream_submit, trk.lib.pam_stream_wait
 
@@ -304,15 +316,15 @@ def parse_state(blob: np.ndarray, S: int, L, cfg):
         tracks = []
         for slot in order:
             m = meta[slot]
-            nviews, hs, hl = int(m[6]), int(m[7]), int(m[8])
-            vc = m[9:9 + L.max_views]
-            vt = m[9 + L.max_views:9 + 2 * L.max_views]
-            ht = m[9 + 2 * L.max_views:9 + 2 * L.max_views + H]
+            nviews, hs, hl, vt_last = int(m[6]), int(m[7]), int(m[8]), int(m[9])
+            vc = m[10:10 + L.max_views]
+            vt = m[10 + L.max_views:10 + 2 * L.max_views]
+            ht = m[10 + 2 * L.max_views:10 + 2 * L.max_views + H]
             poses2d = {int(vc[k]): dict(time=int(vt[k]), pose=view[slot, k].astype(np.float64)) for k in range(nviews)}
             ring = [(hs + i) % H for i in range(hl)]
             poses3d = [dict(time=int(ht[r]), pose3d=hist[slot, r].copy()) for r in ring]
             tracks.append(dict(track_id=int(m[0]), hits=int(m[1]), age=int(m[2]), time_since_update=int(m[3]),
                                state=int(m[4]), already_update=bool(m[5]), poses2d=poses2d, poses3d=poses3d,
-                               velocity_3d=vel[slot].copy(), joint_views=nv[slot].copy()))
+                               velocity_3d=vel[slot].copy(), joint_views=nv[slot].copy(), views_used=vt_last))
         seqs.append(dict(tracks=tracks, next_id=next_id, status=status, warn=warn, warn_frames=int(hdr[6])))
     return seqs

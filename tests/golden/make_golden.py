@@ -180,9 +180,45 @@ def make_functions():
     print("functions.npz written:", len(out), "arrays")
 
 
+def make_results():
+    """results.pkl.gz: the tuple the reference's facade returns per frame (src/ivclabpose.py:216-287,
+    PersonTrack_Project3DPose run UNMODIFIED on top of the unmodified tracker) for the first golden stream: camera ids
+    and 2-D poses matched this frame per track (dict-insertion order), person ids, 3-D poses (n, 3, J), joints_views,
+    3-D person ids."""
+    import pickle
+    shape, seq, T, kw = STREAMS[0]
+    st = synth.make_stream(shape, seq, T, **kw)
+    V = st.shape.V
+    ns = ref_loader.load()
+    cls = ns.ivclabpose.ivclabpose
+    fac = cls.__new__(cls)                                   # skip the CNN-loading constructor
+    fac.cameras = ref_loader.make_cameras(st.rig["P"], st.rig["K"], st.rig["RT"])
+    fac.tracker = ref_loader.make_tracker(synth.tracker_params(shape))
+    frames = []
+    for t in range(T):
+        dets = st.frame_detections(t)
+        person_bbox_list, dump_results = [], []
+        for c in range(V):
+            # the facade swaps columns 0 and 1 of the pose-net keypoints (ivclabpose.py:238-244): hand it (u, v, .)
+            items = [{"bbox": [0, 0, 1, 1], "keypoints": np.stack([d[:, 1], d[:, 0], d[:, 2]], 1).reshape(-1).tolist(),
+                      "keypoints_score": d[:, 2].tolist(), "feature": [0.0]} for d in dets[c]]
+            person_bbox_list.append([{"data": None}] * len(items))
+            dump_results.append(items)
+        cam_ids, pts, person_ids, pts3d, jviews, p3ids, _, _, _ = fac.PersonTrack_Project3DPose(t, person_bbox_list, dump_results, "SVD")
+        frames.append(dict(camera_ids=[list(map(int, x)) for x in cam_ids], pts=[[np.asarray(p, np.float32) for p in x] for x in pts],   # float32-exact values
+                           person_ids=[list(map(int, x)) for x in person_ids], pts3d=np.asarray(pts3d, np.float64),
+                           joints_views=[[list(map(int, b)) for b in jv] for jv in jviews],
+                           person3d_ids=[int(x) for x in p3ids]))
+    import gzip
+    with gzip.open(os.path.join(HERE, "results.pkl.gz"), "wb") as f:
+        pickle.dump(dict(shape=shape, seq=seq, T=T, kw=kw, frames=frames), f, protocol=4)
+    print("results.pkl.gz:", T, "frames,", sum(len(fr["person3d_ids"]) for fr in frames), "reported tracks")
+
+
 if __name__ == "__main__":
     assert ref_loader.available(), "the golden vectors can only be generated where /root/reference exists"
     import warnings
     warnings.filterwarnings("ignore")
     make_streams()
     make_functions()
+    make_results()

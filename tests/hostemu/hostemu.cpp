@@ -10,11 +10,12 @@
 #include "../../part-aware_measurement_for_3d_pose_estimation_and_tracking_b200/csrc/pam_host.h"
 
 using namespace pam;
+bool pam::HostCtx::kTwoPassAffinity = false;
 
 template <class K>
 static int run_sequences(const DevCfg& c, const CamConst& cc, char* state, int S, int T, int frame0, const float* dets,
                          const int32_t* counts, int32_t* out_count, int32_t* out_ids, float* out_joints,
-                         uint8_t* out_nviews, int32_t* out_assoc, int32_t* status) {
+                         uint8_t* out_nviews, int32_t* out_assoc, int32_t* status, uint8_t* out_vlist) {
     std::vector<double> arena((size_t)c.arena_bytes / 8 + 16);
     std::vector<CamShared<K>> cam(1);
     HostCtx ctx;
@@ -30,11 +31,12 @@ static int run_sequences(const DevCfg& c, const CamConst& cc, char* state, int S
             const int64_t ft = (int64_t)s * T + t;
             FrameOut o;
             o.count = out_count + ft;
-            o.ids = out_ids ? out_ids + ft * c.max_trk : nullptr;
-            o.joints = out_joints ? out_joints + ft * c.max_trk * c.J * 3 : nullptr;
-            o.nviews = out_nviews ? out_nviews + ft * c.max_trk * c.J : nullptr;
+            o.ids = out_ids ? out_ids + ft * c.max_rep : nullptr;
+            o.joints = out_joints ? out_joints + ft * c.max_rep * c.J * 3 : nullptr;
+            o.nviews = out_nviews ? out_nviews + ft * c.max_rep * c.J : nullptr;
             o.assoc = out_assoc ? out_assoc + ft * c.V * c.D : nullptr;
             o.timing = nullptr;
+            o.vlist = out_vlist ? out_vlist + ft * c.max_rep * PAM_VLIST : nullptr;
             frame_step(ctx, c, sq, frame0 + t, dets + ft * fstride, counts + ft * c.V, o,
                        dets + (int64_t)s * T * fstride, frame0, hook);
         }
@@ -49,7 +51,8 @@ extern "C" int hostemu_track_sequences(const pam_config* cfg, const float* P, co
                                        const float* F, int S, int T, int frame0, const float* dets,
                                        const int32_t* counts, int32_t* out_count, int32_t* out_ids,
                                        float* out_joints, uint8_t* out_nviews, int32_t* out_assoc,
-                                       int32_t* status, void* state_io /* may be null; S*seq_bytes, zero = fresh */) {
+                                       int32_t* status, void* state_io /* may be null; S*seq_bytes, zero = fresh */,
+                                       uint8_t* out_vlist /* may be null */) {
     DevCfg c;
     std::string err;
     // PAM_HOSTEMU_LEAN=1: the throughput flavour of the working set (one detection buffer, raw pose in the
@@ -60,6 +63,8 @@ extern "C" int hostemu_track_sequences(const pam_config* cfg, const float* P, co
     int rc = make_devcfg(*cfg, c, err, is_lean ? 1 : 2, !is_lean);
     if (rc != PAM_OK) return rc;
     if (!tracker_capable(*cfg)) return PAM_E_INVALID;
+    const char* tp = getenv("PAM_HOSTEMU_TWOPASS");      // the throughput launches' two-pass affinity
+    HostCtx::kTwoPassAffinity = tp && tp[0] == '1';
     const char* fc = getenv("PAM_HOSTEMU_CAPS");
     if (fc && atoi(fc) > c.caps) force_caps(c, atoi(fc));
     std::vector<char> own;
@@ -67,10 +72,10 @@ extern "C" int hostemu_track_sequences(const pam_config* cfg, const float* P, co
     if (!state) { own.assign((size_t)c.seq_bytes * S, 0); state = own.data(); }
     CamConst cc{P, RKinv, pos, F};
     if (c.caps == CAPS_SMALL)
-        return run_sequences<CapsSmall>(c, cc, state, S, T, frame0, dets, counts, out_count, out_ids, out_joints, out_nviews, out_assoc, status);
+        return run_sequences<CapsSmall>(c, cc, state, S, T, frame0, dets, counts, out_count, out_ids, out_joints, out_nviews, out_assoc, status, out_vlist);
     if (c.caps == CAPS_MID)
-        return run_sequences<CapsMid>(c, cc, state, S, T, frame0, dets, counts, out_count, out_ids, out_joints, out_nviews, out_assoc, status);
-    return run_sequences<CapsMax>(c, cc, state, S, T, frame0, dets, counts, out_count, out_ids, out_joints, out_nviews, out_assoc, status);
+        return run_sequences<CapsMid>(c, cc, state, S, T, frame0, dets, counts, out_count, out_ids, out_joints, out_nviews, out_assoc, status, out_vlist);
+    return run_sequences<CapsMax>(c, cc, state, S, T, frame0, dets, counts, out_count, out_ids, out_joints, out_nviews, out_assoc, status, out_vlist);
 }
 
 // decision margins of the sequences in `state` (PAM_MARGIN builds of the harness)

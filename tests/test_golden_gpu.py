@@ -95,3 +95,36 @@ def test_dropin_functions_match_reference_vectors():
         nvj[js] = k + 1
     assert np.array_equal(nvj, z["hyp_views"])
     assert np.allclose([K.get_believe(z["pa"][0]), K.get_believe(z["pb"][1])], z["believe"])
+
+
+def test_result_packing_equals_the_reference_facade():
+    """f2 parity on the device: results.person_track_output on libpam's outputs (incl. the view-list output) equals
+    the tuple the UNMODIFIED PersonTrack_Project3DPose returned (src/ivclabpose.py:259-287), frame by frame; the
+    drop-in IterTrack objects carry the same joints_views / poses2d order."""
+    import torch
+    from pam_b200 import tracker
+    g = util.golden_results()
+    st = synth.make_stream(g["shape"], g["seq"], g["T"], **g["kw"])
+    cams = camera.GetCameraParameters(st.rig)
+    trk = tracker.SequenceTracker(cams, synth.tracker_params(st.shape), 1, max_detections=st.dets.shape[2], max_tracks=12,
+                                  arm_joints=st.shape.arm_joints)
+    out = trk.run(torch.from_numpy(st.dets[None]).cuda(), torch.from_numpy(st.counts[None]).cuda(), nviews=True,
+                  assoc=True, vlist=True)
+    assert trk.check().tolist() == [0]
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    util.check_results_against_facade(out, st.dets[None], g)
+    host = trk.run_host(st.dets[None], st.counts[None], fresh=True, assoc=True, vlist=True)
+    util.check_results_against_facade(host, st.dets[None], g)
+    # the per-frame drop-in: what the facade's loop reads from tracker.tracks (ivclabpose.py:265-283)
+    D = util.load_dropin()
+    from types import SimpleNamespace
+    dt = D.IterativeTracker.IterativeTracker(SimpleNamespace(**synth.tracker_params(st.shape)))
+    for t in range(0, 40):
+        dt.tracking(t, cams, [None] * len(cams), st.frame_boxes(t), st.frame_detections(t), "SVD")
+        fr = g["frames"][t]
+        rep = [tr for tr in dt.tracks if tr.time_since_update == 0 and tr.is_confirmed()]
+        assert [tr.track_id for tr in rep] == fr["person3d_ids"], t
+        for tr, jv, cam_ids, pids in zip(rep, fr["joints_views"], fr["camera_ids"], fr["person_ids"]):
+            assert tr.poses3d[-1]["joints_views"] == jv, t
+            assert [cid for cid, v in tr.poses2d.items() if v["time"] == t] == cam_ids, t
+            assert len(tr.poses2d) == len(pids), t

@@ -50,7 +50,7 @@ def test_kernel_source_chunked_launches_carry_state():
         rc = lib.hostemu_track_sequences(C.byref(cfg), util.ptr(P), util.ptr(RK), util.ptr(pos), util.ptr(F), 1, b - a, a,
                                          util.ptr(dets), util.ptr(counts), util.ptr(out["count"]), util.ptr(out["ids"]),
                                          util.ptr(out["joints"]), util.ptr(out["nviews"]), util.ptr(out["assoc"]),
-                                         util.ptr(status), util.ptr(state))
+                                         util.ptr(status), util.ptr(state), util.ptr(out["vlist"]))
         assert rc == 0 and status[0] == 0
         parts.append(out)
     for k in ("count", "assoc"):

@@ -40,3 +40,16 @@ def test_person_track_output_and_pickle(tmp_path):
     import json
     j = json.load(open(tmp_path / "trk" / "Camera0.json"))
     assert j["image_wh"] == [480, 640] and len(j["frames"]) == 1
+
+
+def test_person_track_output_equals_the_reference_facade_hostemu():
+    """f2 parity: the tuple packed from the kernel's outputs (kernel source on the host)
+    equals what the UNMODIFIED PersonTrack_Project3DPose returned on top of the unmodified tracker, frame by frame:
+    camera ids in dict-insertion order, person ids per view-dict entry, joints_views buckets, 3-D poses."""
+    from tests import util
+    from pam_b200 import synth
+    g = util.golden_results()
+    st = synth.make_stream(g["shape"], g["seq"], g["T"], **g["kw"])
+    out = util.run_hostemu([st], util.stream_config(st, max_tracks=12))
+    assert out["status"].tolist() == [0]
+    util.check_results_against_facade(out, st.dets[None], g)

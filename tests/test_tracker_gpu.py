@@ -153,3 +153,30 @@ def test_every_launch_shape_matches_oracle(env, monkeypatch):
     for s, st in enumerate(streams):
         oo, oa, _ = util.run_oracle(st)
         util.compare_with_oracle(out, s, st, oo, oa)
+
+
+def test_max_report_only_changes_the_output_stride():
+    """pam_config.max_report: fewer output rows per frame (less D2H traffic); the rows kept are the first rows of the
+    full output, `count` keeps the true number."""
+    import torch
+    st = synth.make_stream("shelf", 9, 120, miss_prob=0.05, outlier_prob=0.03)
+    cams = camera.GetCameraParameters(st.rig)
+    kw = dict(max_detections=st.dets.shape[2], max_tracks=8, arm_joints=st.shape.arm_joints)
+    full = tracker.SequenceTracker(cams, synth.tracker_params("shelf"), 1, **kw)
+    cut = tracker.SequenceTracker(cams, synth.tracker_params("shelf"), 1, max_report=3, **kw)
+    d, c = torch.from_numpy(st.dets[None]).cuda(), torch.from_numpy(st.counts[None]).cuda()
+    a = {k: v.cpu().numpy() for k, v in full.run(d, c, assoc=True, vlist=True).items()}
+    b = {k: v.cpu().numpy() for k, v in cut.run(d, c, assoc=True, vlist=True).items()}
+    assert b["ids"].shape[2] == 3 and b["joints"].shape[2] == 3 and b["nviews"].shape[2] == 3 and b["vlist"].shape[2] == 3
+    assert np.array_equal(a["count"], b["count"]) and np.array_equal(a["assoc"], b["assoc"]) and a["count"].max() == 4
+    for t in range(st.T):
+        r = min(3, a["count"][0, t])
+        for k in ("ids", "joints", "nviews", "vlist"):
+            assert np.array_equal(a[k][0, t, :r], b[k][0, t, :r]), (k, t)
+    h = cut.run_host(st.dets[None], st.counts[None], fresh=True, assoc=True, vlist=True)
+    for k in ("count", "assoc"):
+        assert np.array_equal(h[k], b[k])
+    for t in range(st.T):
+        r = min(3, a["count"][0, t])
+        for k in ("ids", "joints", "nviews", "vlist"):
+            assert np.array_equal(h[k][0, t, :r], b[k][0, t, :r]), (k, t)

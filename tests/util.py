@@ -25,7 +25,8 @@ def alloc_outputs(cfg, S, T, want_assoc=True):
     MT, J, V, D = cfg.max_tracks, cfg.num_joints, cfg.num_cameras, cfg.max_detections
     return dict(count=np.zeros((S, T), np.int32), ids=np.full((S, T, MT), -1, np.int32),
                 joints=np.zeros((S, T, MT, J, 3), np.float32), nviews=np.zeros((S, T, MT, J), np.uint8),
-                assoc=np.full((S, T, V, D), -1, np.int32) if want_assoc else None)
+                assoc=np.full((S, T, V, D), -1, np.int32) if want_assoc else None,
+                vlist=np.zeros((S, T, MT, 10), np.uint8))
 
 
 def run_hostemu(streams, cfg, frame0=0):
@@ -41,7 +42,7 @@ def run_hostemu(streams, cfg, frame0=0):
     status = np.zeros(S, np.int32)
     rc = lib.hostemu_track_sequences(C.byref(cfg), ptr(P), ptr(RK), ptr(pos), ptr(F), S, T, frame0, ptr(dets),
                                      ptr(counts), ptr(out["count"]), ptr(out["ids"]), ptr(out["joints"]),
-                                     ptr(out["nviews"]), ptr(out["assoc"]), ptr(status), None)
+                                     ptr(out["nviews"]), ptr(out["assoc"]), ptr(status), None, ptr(out["vlist"]))
     assert rc == 0, rc
     out["status"] = status
     return out
@@ -104,6 +105,29 @@ def golden_as_oracle_lists(g):
     frames = [(g["ids"][t, :g["count"][t]], g["joints"][t, :g["count"][t]], g["views"][t, :g["count"][t]]) for t in range(T)]
     assoc = [[g["assoc"][t, c] for c in range(g["assoc"].shape[1])] for t in range(T)]
     return frames, assoc
+
+
+def golden_results():
+    """The reference facade's per-frame return tuple for the first golden stream (tests/golden/make_golden.py)."""
+    import gzip
+    import pickle
+    with gzip.open(_os.path.join(GOLDEN, "results.pkl.gz"), "rb") as f:
+        return pickle.load(f)
+
+
+def check_results_against_facade(out, dets, g):
+    """results.person_track_output on tracker outputs (count, ids, joints, nviews, assoc, vlist) against the tuple
+    PersonTrack_Project3DPose returned for the same stream (src/ivclabpose.py:259-287)."""
+    from pam_b200 import results
+    for t, fr in enumerate(g["frames"]):
+        cam_ids, pts, person_ids, pts3d, jviews, p3ids = results.person_track_output(out, 0, t, dets=dets)
+        assert [int(x) for x in p3ids] == fr["person3d_ids"], t
+        assert [list(x) for x in cam_ids] == fr["camera_ids"], (t, [list(x) for x in cam_ids], fr["camera_ids"])
+        assert person_ids == fr["person_ids"], t
+        assert jviews == fr["joints_views"], (t, jviews, fr["joints_views"])
+        assert pts3d.shape == fr["pts3d"].shape and (pts3d.size == 0 or np.abs(pts3d - fr["pts3d"]).max() < 5e-4), t
+        for a, b in zip(pts, fr["pts"]):
+            assert len(a) == len(b) and all(np.array_equal(np.asarray(x, np.float32), y) for x, y in zip(a, b)), t
 
 
 def golden_functions():
