@@ -542,6 +542,7 @@ static const TrackVariant k_variants[] = {
     // frames of a CTA started together: 67.7 M frames/s at 16 per SM with 128 registers, 68.9 M at 24 per SM
     // with 80; without the convoy barrier 61.5 M; three warps per sequence at 8 per SM: 59 M)
     PAM_VARIANT(CapsSmall, CAPS_SMALL, 256, 2, 1, 128),
+    PAM_VARIANT(CapsSmall, CAPS_SMALL, 320, 2, 1, 96),
     PAM_VARIANT(CapsSmall, CAPS_SMALL, 384, 2, 1, 80),
     PAM_VARIANT(CapsSmall, CAPS_SMALL, 256, 3, 1, 80),
     // three warps per sequence, one sequence per CTA, 8 CTAs per SM: 5-11 sequences per SM

@@ -589,24 +589,18 @@ __global__ void k_hypothesis_cost(const float* __restrict__ F, int V, const doub
 // remap 1: COCO-17 -> Shelf-14 with coco2shelf3D (eval/transformation.py:5-39).
 // counters [P][10][2] int64 = (correct, evaluated) per actor and bone (9 limbs + hip-head), summed over
 // all sequences / frames with atomics; mpjpe [2] f64 = (sum of per-joint errors, joints counted).
-// Shelf-14 joint j of a predicted pose p [J][3] f32, computed on demand (no per-thread pose arrays: the kernel is
-// bandwidth bound and needs the occupancy).  remap: COCO-17 -> Shelf-14 (eval/transformation.py:5-39).
-__device__ __forceinline__ void shelf14_joint(const float* __restrict__ p, int remap, int j, double* o) {
+__device__ __forceinline__ void to_shelf14(const float* __restrict__ p, int remap, double (*o)[3]) {
     if (!remap) {
-        o[0] = (double)p[j * 3]; o[1] = (double)p[j * 3 + 1]; o[2] = (double)p[j * 3 + 2];
+        for (int j = 0; j < 14; ++j) for (int k = 0; k < 3; ++k) o[j][k] = (double)p[j * 3 + k];
         return;
     }
     const int map[12] = {16, 14, 12, 11, 13, 15, 10, 8, 6, 5, 7, 9};
-    if (j < 12) {
-        const float* q = p + map[j] * 3;
-        o[0] = (double)q[0]; o[1] = (double)q[1]; o[2] = (double)q[2];
-        return;
-    }
+    for (int j = 0; j < 12; ++j) for (int k = 0; k < 3; ++k) o[j][k] = (double)p[map[j] * 3 + k];
     const double top[3] = {0.78, 0.5, 1.5}, bot[3] = {0.3, 0.4, 0.6};
-#pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const double mid = ((double)p[6 * 3 + k] + (double)p[5 * 3 + k]) / 2.0, nose = (double)p[k];   // shelf joints 8, 9
-        o[k] = mid + (nose - mid) * (j == 13 ? top[k] : bot[k]);
+        const double mid = (o[8][k] + o[9][k]) / 2.0, nose = (double)p[k];
+        o[13][k] = mid + (nose - mid) * top[k];
+        o[12][k] = mid + (nose - mid) * bot[k];
     }
 }
 __device__ __forceinline__ double dist3(const double* a, const double* b) {
@@ -614,10 +608,23 @@ __device__ __forceinline__ double dist3(const double* a, const double* b) {
     return sqrt(x * x + y * y + z * z);
 }
 #define PAM_EVAL_MAX_P 64
-__global__ void __launch_bounds__(128, 5)
+#define PAM_EVAL_THREADS 128
+#define PAM_EVAL_GT_STRIDE 43      // doubles per staged ground-truth pose (42 + 1: odd stride, no bank conflicts)
+// Dynamic shared memory: the block's 128 ground-truth poses [128][43] f64, then the predicted poses of the frames
+// they belong to [frames][MT][J][3] f32.  Both are contiguous in HBM, so they are staged with fully coalesced loads
+// (the kernel is bandwidth bound: 1344 B of ground truth + up to MT x J x 12 B of predictions per frame); the
+// arithmetic then runs out of shared memory.
+__host__ __device__ inline int eval_frames_per_block(int P) { return (PAM_EVAL_THREADS + P - 1) / P + 1; }
+__host__ __device__ inline size_t eval_smem_bytes(int P, int MT, int J) {
+    return (size_t)PAM_EVAL_THREADS * PAM_EVAL_GT_STRIDE * 8 + (size_t)eval_frames_per_block(P) * MT * J * 3 * 4;
+}
+__global__ void __launch_bounds__(PAM_EVAL_THREADS)
 k_eval_pcp(const int* __restrict__ count, const float* __restrict__ joints, const double* __restrict__ gt,
            const unsigned char* __restrict__ gt_valid, int S, int T, int P, int MT, int J, int remap,
            int t0, int t1, double alpha, unsigned long long* __restrict__ counters, double* __restrict__ mpjpe) {
+    extern __shared__ __align__(16) unsigned char eval_smem[];
+    double* s_gt = (double*)eval_smem;
+    float* s_pred = (float*)(s_gt + PAM_EVAL_THREADS * PAM_EVAL_GT_STRIDE);
     // block-local counters first (shared-memory atomics), one global atomic per counter per block
     __shared__ unsigned int s_cnt[PAM_EVAL_MAX_P * 20];
     __shared__ double s_err[4];
@@ -625,11 +632,34 @@ k_eval_pcp(const int* __restrict__ count, const float* __restrict__ joints, cons
     for (int i = threadIdx.x; i < P * 20; i += blockDim.x) s_cnt[i] = 0u;
     if (threadIdx.x < 4) s_err[threadIdx.x] = 0.0;
     if (threadIdx.x == 0) s_nj = 0u;
+    const int64_t total = (int64_t)S * T * P;
+    const int64_t item0 = (int64_t)blockIdx.x * PAM_EVAL_THREADS;
+    const int nitems = (int)((total - item0) < PAM_EVAL_THREADS ? (total - item0) : PAM_EVAL_THREADS);
+    const int64_t frame0 = item0 / P, frame1 = (item0 + nitems - 1) / P;       // flattened (sequence, frame) indices
+    const int nframes = (int)(frame1 - frame0 + 1);
+    {   // ground truth: nitems x 42 contiguous doubles -> padded rows
+        const double* src = gt + item0 * 42;
+        for (int i = threadIdx.x; i < nitems * 42; i += PAM_EVAL_THREADS) {
+            const int r = i / 42, e = i - r * 42;
+            s_gt[r * PAM_EVAL_GT_STRIDE + e] = src[i];
+        }
+        // predictions: nframes x MT x J x 3 contiguous floats
+        const int row = MT * J * 3;
+        const float* ps = joints + frame0 * row;
+        const int n = nframes * row;
+        if ((((uintptr_t)ps) & 15) == 0 && (n & 3) == 0) {
+            const float4* p4 = (const float4*)ps;
+            float4* d4 = (float4*)s_pred;
+            for (int i = threadIdx.x; i < n / 4; i += PAM_EVAL_THREADS) d4[i] = p4[i];
+        } else {
+            for (int i = threadIdx.x; i < n; i += PAM_EVAL_THREADS) s_pred[i] = ps[i];
+        }
+    }
     __syncthreads();
-    const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t it = item0 + threadIdx.x;
     double e = 0.0;
     bool scored = false;
-    if (it < (int64_t)S * T * P) {
+    if (it < total) {
         const int pid = (int)(it % P);
         const int64_t st = it / P;
         const int t = (int)(st % T);
@@ -639,47 +669,31 @@ k_eval_pcp(const int* __restrict__ count, const float* __restrict__ joints, cons
             if (k <= 0) {                  // "Cannot get any pose in frame": all ten parts count as errors
                 for (int b = 0; b < 10; ++b) atomicAdd(cnt + b * 2 + 1, 1u);
             } else {
-                const double* g = gt + it * 14 * 3;
-                // closest prediction (vectorize_distance: squared distance over all 42 coordinates, first minimum)
-                double best = 0.0;
+                const double* g = s_gt + threadIdx.x * PAM_EVAL_GT_STRIDE;
+                const float* pf = s_pred + (int64_t)(st - frame0) * MT * J * 3;
+                double best = 0.0, bm[14][3];
                 int bq = 0;
                 for (int q = 0; q < k; ++q) {
-                    const float* pq = joints + ((int64_t)st * MT + q) * J * 3;
-                    double d = 0.0;
-#pragma unroll 2
-                    for (int j = 0; j < 14; ++j) {
-                        double m[3];
-                        shelf14_joint(pq, remap, j, m);
-                        for (int c = 0; c < 3; ++c) { const double x = g[j * 3 + c] - m[c]; d += x * x; }
-                    }
+                    to_shelf14(pf + q * J * 3, remap, bm);
+                    double d = 0.0;        // vectorize_distance: squared distance over all 42 coordinates
+                    for (int j = 0; j < 14; ++j)
+                        for (int c = 0; c < 3; ++c) { const double x = g[j * 3 + c] - bm[j][c]; d += x * x; }
                     if (q == 0 || d < best) { best = d; bq = q; }
                 }
-                const float* pb = joints + ((int64_t)st * MT + bq) * J * 3;
-                // per-joint error of the chosen prediction: all the limb tests and the MPJPE need
-                double err[14];
-#pragma unroll
-                for (int j = 0; j < 14; ++j) {
-                    double m[3];
-                    shelf14_joint(pb, remap, j, m);
-                    err[j] = dist3(g + j * 3, m);
-                }
+                to_shelf14(pf + bq * J * 3, remap, bm);      // the closest prediction again (shared memory: cheap)
                 const int bones[9][2] = {{0, 1}, {1, 2}, {3, 4}, {4, 5}, {6, 7}, {7, 8}, {9, 10}, {10, 11}, {12, 13}};
-#pragma unroll
                 for (int b = 0; b < 9; ++b) {
                     const int s0 = bones[b][0], e0 = bones[b][1];
                     const double len = dist3(g + e0 * 3, g + s0 * 3);
-                    if ((err[s0] + err[e0]) / 2.0 <= alpha * len) atomicAdd(cnt + b * 2, 1u);
+                    if ((dist3(g + s0 * 3, bm[s0]) + dist3(g + e0 * 3, bm[e0])) / 2.0 <= alpha * len) atomicAdd(cnt + b * 2, 1u);
                     atomicAdd(cnt + b * 2 + 1, 1u);
                 }
-                double gh[3], mh[3], m2[3], m3[3];
-                shelf14_joint(pb, remap, 2, m2);
-                shelf14_joint(pb, remap, 3, m3);
-                for (int c = 0; c < 3; ++c) { gh[c] = (g[2 * 3 + c] + g[3 * 3 + c]) / 2.0; mh[c] = (m2[c] + m3[c]) / 2.0; }
+                double gh[3], mh[3];
+                for (int c = 0; c < 3; ++c) { gh[c] = (g[2 * 3 + c] + g[3 * 3 + c]) / 2.0; mh[c] = (bm[2][c] + bm[3][c]) / 2.0; }
                 const double len = dist3(g + 12 * 3, gh);
-                if ((dist3(gh, mh) + err[12]) / 2.0 <= alpha * len) atomicAdd(cnt + 18, 1u);
+                if ((dist3(gh, mh) + dist3(g + 12 * 3, bm[12])) / 2.0 <= alpha * len) atomicAdd(cnt + 18, 1u);
                 atomicAdd(cnt + 19, 1u);
-#pragma unroll
-                for (int j = 0; j < 14; ++j) e += err[j];
+                for (int j = 0; j < 14; ++j) e += dist3(g + j * 3, bm[j]);
                 scored = true;
             }
         }

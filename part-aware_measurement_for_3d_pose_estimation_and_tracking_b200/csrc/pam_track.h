@@ -22,6 +22,11 @@
 #pragma once
 #include "pam_core.h"
 
+// views / view pairs in flight per thread in the part-aware filter and the Gram fold (phase 5)
+#if !defined(PAM_P5_UNROLL)
+#define PAM_P5_UNROLL 1
+#endif
+
 namespace pam {
 
 enum { ST_TENTATIVE = 1, ST_CONFIRMED = 2, ST_DELETED = 3 };
@@ -420,7 +425,7 @@ PAM_HD void dlt_from_views(const Seq<K>& sq, int Vt, const Views& vw, uint32_t a
     DltAccum acc;
     int path = -1;
     acc.reset(true);
-    PAM_NOUNROLL for (int a = 0; a < Vt; ++a)
+    PAM_UNROLL_N(PAM_P5_UNROLL) for (int a = 0; a < Vt; ++a)
         if ((alive >> a) & 1u) acc.add_view(sq.Pc(vw.cid(a)), vw.u(a), vw.v(a), vw.w(a));
     acc.solve(X, &path);
     if (path < 0) {
@@ -441,7 +446,7 @@ PAM_HD int joint_update(const DevCfg& c, const Seq<K>& sq, int Vt, const SrcView
     PAM_NOUNROLL for (int a = 0; a < Vt; ++a) {
         const double ua = vw.u(a), va = vw.v(a);
         const int ca = vw.cid(a);
-        PAM_NOUNROLL for (int b = a + 1; b < Vt; ++b) {
+        PAM_UNROLL_N(PAM_P5_UNROLL) for (int b = a + 1; b < Vt; ++b) {
             const double ub = vw.u(b), vb = vw.v(b);
             const int cb = vw.cid(b);
             double tab, nab, tba, nba;

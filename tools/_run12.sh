@@ -8,4 +8,10 @@ for ln in sys.stdin:
     i = r['info']
     print(r['config'], round(r['ms'],1), 'ms', round(r['mfps'],1), 'M', 'G%d Q%d regs%d ctas/SM %d smem %d nbuf %d' % (i['warps_per_sequence'], i['sequences_per_cta'], i['registers_per_thread'], i['ctas_per_sm'], i['smem_per_cta'], i['detection_buffers']), r['identical_to_first'], r['clocks'])
 "
-timeout 300 python -m pytest tests/test_tracker_gpu.py tests/test_fuzz_hostemu.py tests/test_evaluate.py -m gpu -x -q 2>&1 | tail -3
+timeout 600 python -m pytest tests -m gpu -x -q -k "not full_length_oracle" 2>&1 | tail -3
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench12.json 2> gpurun_out/bench12.err; tail -c 400 gpurun_out/bench12.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench12.json').read().strip().splitlines()[-1])
+print("value", d["value"]/1e6, "kernel_ms", d["roofline"]["kernel_ms"], "ms/step", d["ms_per_step"], "e2e", d["e2e"]["value"]/1e6, "parity", d["parity_sample"], "per_frame", d["per_frame_api"]["value"], d["per_frame_api"]["stream_mode"]["value"])
+PY
