@@ -308,6 +308,23 @@ int pam_eval_panoptic_match(pam_handle* h, const int32_t* d_out_count, const flo
                             const uint8_t* d_gt_vis, const int32_t* d_n_gt, int32_t S, int32_t T, int32_t max_gt,
                             int32_t max_tracks, double* d_mpjpe, int32_t* d_gt_index, void* stream);
 
+/* ---- alternatives the reference keeps in its API without a live caller ----------- */
+
+/* One-Euro filter bank (tracking/OneEuroFilter.py:12-77): n channels sharing their time stamps, e.g. the 3 x J
+ * coordinates of one track (tracking/IterativeTracker.py:231-237).  d_state [n][4] f64 = {last raw value, filtered value,
+ * filtered derivative, initialised (0/1)}, zero = fresh; `freq` is kept by the caller like the reference keeps it
+ * (1 / (t - t_last) once both time stamps are truthy).  d_out [n] = filtered values; bit-identical to the python class. */
+int pam_one_euro(pam_handle* h, const double* d_x, int32_t n, double freq, double mincutoff, double beta, double dcutoff,
+                 double* d_state, double* d_out, void* stream);
+
+/* top_down_pose_kernel (utils/construction.py:9-31): every camera pair triangulates all joints from its two views
+ * (cv2.triangulatePoints' 4 x 4 system); the pair whose pose reprojects best into all cameras wins.
+ * d_poses2d [batch][n_views][J][2] f64 (x, y), d_cam [batch][n_views] i32 -> d_pose3d [batch][J][3] f64,
+ * d_pair_or_null [batch][2] i32 (the winning views), d_err_or_null [batch][n_views (n_views - 1) / 2] f64 (the summed
+ * reprojection error of every pair, pairs in (0,1), (0,2), ... order). */
+int pam_top_down(pam_handle* h, const double* d_poses2d, const int32_t* d_cam, int32_t batch, int32_t n_views,
+                 double* d_pose3d, int32_t* d_pair_or_null, double* d_err_or_null, void* stream);
+
 /* number of kernel launches issued through this handle so far (bench.py "gpu_launches") */
 int64_t pam_launch_count(const pam_handle* h);
 

@@ -443,6 +443,15 @@ struct DltAccum {
         x[0] = V[0][arg]; x[1] = V[1][arg]; x[2] = V[2][arg]; x[3] = V[3][arg];
     }
 
+    // homogeneous solution of a Gram-accumulated system: unit 4-vector with a positive last component (the
+    // convention of the pair-wise triangulation below); false when the system is singular
+    PAM_HD bool solve_homog(double* x) {
+        if (gram && !cholesky()) return false;
+        if (!invit(x)) jacobi(x);
+        if (x[3] < 0.0) { x[0] = -x[0]; x[1] = -x[1]; x[2] = -x[2]; x[3] = -x[3]; }
+        return true;
+    }
+
     // de-homogenised joint.  `path` (optional) reports which extractor produced it (tests).
     PAM_HD void solve(double* X, int* path = nullptr) {
         double x[4];

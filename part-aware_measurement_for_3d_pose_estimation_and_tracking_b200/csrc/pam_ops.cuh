@@ -761,4 +761,108 @@ __global__ void k_eval_panoptic_match(const int* __restrict__ count, const float
     out_gt[it] = arg;
 }
 
+// ---- section 8f-4: the reference's alternative smoother and pair-wise triangulation (no live caller) ----------
+
+// One-Euro filter bank (tracking/OneEuroFilter.py:12-77): n channels that share their time stamps (the way IterTrack
+// holds one filter per joint coordinate, tracking/IterativeTracker.py:231-237).  state [n][4] f64 = {last raw value,
+// filtered value, filtered derivative, initialised}; `freq` is maintained by the host exactly like the reference
+// (1 / (t - t_last) once both are truthy).  IEEE operations in the reference's order, no FMA contraction: bit-identical
+// to the python class.
+__device__ __forceinline__ double one_euro_alpha(double freq, double cutoff) {
+    const double te = __ddiv_rn(1.0, freq);
+    const double tau = __ddiv_rn(1.0, __dmul_rn(6.283185307179586, cutoff));      // 2 * math.pi * cutoff
+    return __ddiv_rn(1.0, __dadd_rn(1.0, __ddiv_rn(tau, te)));
+}
+__global__ void k_one_euro(int n, const double* __restrict__ x, double freq, double mincutoff, double beta, double dcutoff,
+                           double* __restrict__ state, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* st = state + (int64_t)i * 4;
+    const bool have = st[3] != 0.0;
+    const double xi = x[i];
+    const double dx = have ? __dmul_rn(__dsub_rn(xi, st[0]), freq) : 0.0;
+    const double ad = one_euro_alpha(freq, dcutoff);
+    const double edx = have ? __dadd_rn(__dmul_rn(ad, dx), __dmul_rn(__dsub_rn(1.0, ad), st[2])) : dx;
+    const double cutoff = __dadd_rn(mincutoff, __dmul_rn(beta, fabs(edx)));
+    const double a = one_euro_alpha(freq, cutoff);
+    const double s = have ? __dadd_rn(__dmul_rn(a, xi), __dmul_rn(__dsub_rn(1.0, a), st[1])) : xi;
+    st[0] = xi; st[1] = s; st[2] = edx; st[3] = 1.0;
+    out[i] = s;
+}
+
+// top_down_pose_kernel (utils/construction.py:9-31): every camera pair triangulates all joints from its two views
+// (the 4 x 4 homogeneous system of cv2.triangulatePoints: rows x P2 - P0, y P2 - P1 of both views, not normalised);
+// the pair whose 3-D pose reprojects best into ALL cameras -- sum over cameras of the Frobenius norm of the (J, 2)
+// residual, with the reference's "+ 10e-6" on the homogeneous depth -- wins.
+// One block per batch item; poses2d [batch][V][J][2] (x, y), cam [batch][V]; out pose3d [batch][J][3], pair [batch][2].
+__device__ __forceinline__ bool pair_triangulate(const float* __restrict__ P, int ca, int cb, const double* pa, const double* pb,
+                                                 double* xh) {
+    double Pa[12], Pb[12];
+    load12(P + ca * 12, Pa);
+    load12(P + cb * 12, Pb);
+    DltAccum acc;
+    acc.reset(true);
+    acc.add_row(pa[0] * Pa[8] - Pa[0], pa[0] * Pa[9] - Pa[1], pa[0] * Pa[10] - Pa[2], pa[0] * Pa[11] - Pa[3]);
+    acc.add_row(pa[1] * Pa[8] - Pa[4], pa[1] * Pa[9] - Pa[5], pa[1] * Pa[10] - Pa[6], pa[1] * Pa[11] - Pa[7]);
+    acc.add_row(pb[0] * Pb[8] - Pb[0], pb[0] * Pb[9] - Pb[1], pb[0] * Pb[10] - Pb[2], pb[0] * Pb[11] - Pb[3]);
+    acc.add_row(pb[1] * Pb[8] - Pb[4], pb[1] * Pb[9] - Pb[5], pb[1] * Pb[10] - Pb[6], pb[1] * Pb[11] - Pb[7]);
+    return acc.solve_homog(xh);
+}
+__global__ void __launch_bounds__(128)
+k_top_down(const float* __restrict__ P, const double* __restrict__ poses2d, const int* __restrict__ cam, int V, int J,
+           double* __restrict__ out_pose, int* __restrict__ out_pair, double* __restrict__ out_err) {
+    extern __shared__ double s_err[];                      // [pairs][V] squared residuals per (pair, camera)
+    const int b = blockIdx.x;
+    const double* p2 = poses2d + (int64_t)b * V * J * 2;
+    const int* cm = cam + (int64_t)b * V;
+    const int npairs = V * (V - 1) / 2;
+    // (pair, camera): squared Frobenius residual of the pair's pose in that camera
+    for (int it = threadIdx.x; it < npairs * V; it += blockDim.x) {
+        const int pr = it / V, k = it - pr * V;
+        int i = 0, rem = pr;
+        while (rem >= V - 1 - i) { rem -= V - 1 - i; ++i; }
+        const int j2 = i + 1 + rem;
+        double Pk[12];
+        load12(P + cm[k] * 12, Pk);
+        double acc = 0.0;
+        for (int j = 0; j < J; ++j) {
+            double xh[4];
+            if (!pair_triangulate(P, cm[i], cm[j2], p2 + (i * J + j) * 2, p2 + (j2 * J + j) * 2, xh)) { acc = HUGE_VAL; break; }
+            const double a = Pk[0] * xh[0] + Pk[1] * xh[1] + Pk[2] * xh[2] + Pk[3] * xh[3];
+            const double c2 = Pk[4] * xh[0] + Pk[5] * xh[1] + Pk[6] * xh[2] + Pk[7] * xh[3];
+            const double w = Pk[8] * xh[0] + Pk[9] * xh[1] + Pk[10] * xh[2] + Pk[11] * xh[3] + 10e-6;
+            const double dx = a / w - p2[(k * J + j) * 2], dy = c2 / w - p2[(k * J + j) * 2 + 1];
+            acc += dx * dx + dy * dy;
+        }
+        s_err[it] = acc;
+    }
+    __syncthreads();
+    __shared__ int s_best;
+    if (threadIdx.x == 0) {
+        double best = 0.0;
+        int arg = 0;
+        for (int pr = 0; pr < npairs; ++pr) {
+            double e = 0.0;
+            for (int k = 0; k < V; ++k) e += sqrt(s_err[pr * V + k]);
+            if (out_err) out_err[(int64_t)b * npairs + pr] = e;
+            if (pr == 0 || e < best) { best = e; arg = pr; }       // np.argmin: first minimum
+        }
+        s_best = arg;
+    }
+    __syncthreads();
+    int i = 0, rem = s_best;
+    while (rem >= V - 1 - i) { rem -= V - 1 - i; ++i; }
+    const int j2 = i + 1 + rem;
+    if (threadIdx.x == 0 && out_pair) { out_pair[b * 2] = i; out_pair[b * 2 + 1] = j2; }
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        double xh[4];
+        double* o = out_pose + ((int64_t)b * J + j) * 3;
+        if (pair_triangulate(P, cm[i], cm[j2], p2 + (i * J + j) * 2, p2 + (j2 * J + j) * 2, xh)) {
+            o[0] = xh[0] / xh[3]; o[1] = xh[1] / xh[3]; o[2] = xh[2] / xh[3];
+        } else {
+            o[0] = o[1] = o[2] = nan("");
+        }
+    }
+}
+
 }  // namespace pam

@@ -657,7 +657,7 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
         if (a > 0.0) PAM_NOTE(MG_ASSIGN, a);
         return a;
     };
-    if (Ctx::kTwoPassAffinity && c.aff_probe > 0) {
+    if (Ctx::kTwoPassAffinity && c.aff_probe > 0 && V * n * D > ctx.nthreads()) {      // pays from two sweeps on
         // Throughput launches.  Most (track, detection) pairs belong to different people: after the first
         // `aff_probe` joints such a pair can no longer collect more than min_valid joints with c > 0, so its
         // affinity is exactly 0 (IterativeTracker.py:145-147) and it is dropped.  The survivors -- about one
@@ -997,8 +997,8 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
             unsigned char* vl = out.vlist + sh.out_row[i] * PAM_VLIST;
             vl[0] = (unsigned char)sh.gv_n[i];
             vl[1] = (unsigned char)t.nviews;
-            PAM_NOUNROLL for (int k = 0; k < t.nviews; ++k)
-                vl[2 + k] = (unsigned char)(t.view_cid[k] | (t.view_time[k] == frame ? 0x80 : 0));
+            PAM_NOUNROLL for (int k = 0; k < PAM_MAX_V; ++k)       // the whole row is written (unused entries 0)
+                vl[2 + k] = (k < t.nviews) ? (unsigned char)(t.view_cid[k] | (t.view_time[k] == frame ? 0x80 : 0)) : (unsigned char)0;
         }
         sh.life_flag[i] = (signed char)flag;
     }

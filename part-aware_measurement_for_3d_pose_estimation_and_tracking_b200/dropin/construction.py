@@ -1,4 +1,4 @@
-"""GPU-backed ``construction`` (reference: src/utils/construction.py:64-131)."""
+"""GPU-backed ``construction`` (reference: src/utils/construction.py:9-31, 64-131)."""
 from math import exp
 
 import numpy as np
@@ -49,3 +49,11 @@ def SVD_pose_kernel(cameras, Ts, joints, remains, lambda_t, next_pose=None):
         else:
             res.append(out[j])
     return res
+
+
+def top_down_pose_kernel(cameras, poses2d, weight2d=None):
+    """Pair-wise triangulation, best pair by summed reprojection error (src/utils/construction.py:9-31)
+    -> (pose3d (J, 3), weight of the winning pair)."""
+    p = np.asarray([np.asarray(q, dtype=np.float64) for q in poses2d])
+    pose3d, pair = _ops.get_ops(list(cameras), p.shape[1]).top_down(np.arange(p.shape[0]), p)
+    return pose3d, (weight2d[int(pair[0])] + weight2d[int(pair[1])]) / 2

@@ -218,6 +218,24 @@ class GeometryOps:
             out = out[0]
         return out.cpu().numpy() if as_numpy else out
 
+    # -- f4: alternatives without a live caller in the reference ----------------------------------
+    def top_down(self, cam_index, poses2d, want_errors=False):
+        """``top_down_pose_kernel`` (src/utils/construction.py:9-31): poses2d (B,Vt,J,2) or (Vt,J,2) as (x, y);
+        cam_index (B,Vt)/(Vt,) -> pose3d (B,J,3)/(J,3), winning pair (B,2)/(2,) [, errors (B, Vt(Vt-1)/2)]."""
+        torch = _torch()
+        p = np.asarray(poses2d, dtype=np.float64)
+        single = p.ndim == 3
+        p = self._dev(p[None] if single else p, torch.float64).contiguous()
+        B, Vt = p.shape[0], p.shape[1]
+        cam = self._dev(np.asarray(cam_index), torch.int32).reshape(B, Vt)
+        out = torch.empty((B, self.J, 3), dtype=torch.float64, device=self.dev)
+        pair = torch.empty((B, 2), dtype=torch.int32, device=self.dev)
+        err = torch.empty((B, Vt * (Vt - 1) // 2), dtype=torch.float64, device=self.dev) if want_errors else None
+        self._call(self.lib.pam_top_down, self._p(p), self._p(cam), B, Vt, self._p(out), self._p(pair), self._p(err),
+                   self._stream())
+        res = (out.cpu().numpy(), pair.cpu().numpy()) + ((err.cpu().numpy(),) if want_errors else ())
+        return tuple(r[0] for r in res) if single else res
+
     # -- a16 -------------------------------------------------------------------------------------
     def mean_confidence(self, poses):
         """Batched ``get_believe``: (B,J,3) -> (B,)."""
@@ -276,3 +294,33 @@ def get_ops(cameras: Sequence, num_joints: int, params: Optional[dict] = None) -
 def project_points(cameras, points3d):
     pts = np.asarray(points3d)
     return get_ops(cameras, pts.shape[-2]).project_points(pts)
+
+
+# ------------------------------------------------------------------------------------------------
+# One-Euro filter bank: needs no cameras, so it runs on a bare handle per device
+# ------------------------------------------------------------------------------------------------
+_bare = {}
+
+
+def _bare_handle(device: int = 0):
+    if device not in _bare:
+        lib = _capi.load_library()
+        cfg = _capi.make_config(dict(_DEFAULT_PARAMS, num_joints=1), 1, 1, 1, (), 0)
+        h = C.c_void_p()
+        _check(lib, None, lib.pam_create(C.byref(cfg), int(device), C.byref(h)))
+        _bare[device] = (lib, h)
+    return _bare[device]
+
+
+def one_euro(x, state, freq, mincutoff, beta, dcutoff, device: int = 0):
+    """One step of a One-Euro filter bank (src/tracking/OneEuroFilter.py:60-77): ``x`` (n,) float64, ``state`` a CUDA
+    tensor (n, 4) float64 (zeros = fresh, updated in place) -> filtered values (n,) as numpy."""
+    torch = _torch()
+    lib, h = _bare_handle(device)
+    xd = torch.as_tensor(np.asarray(x, dtype=np.float64).reshape(-1), device=f"cuda:{device}")
+    out = torch.empty_like(xd)
+    st = torch.cuda.current_stream(device).cuda_stream
+    rc = lib.pam_one_euro(h, C.c_void_p(xd.data_ptr()), xd.shape[0], float(freq), float(mincutoff), float(beta),
+                          float(dcutoff), C.c_void_p(state.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(st))
+    _check(lib, h, rc)
+    return out.cpu().numpy()

@@ -15,11 +15,12 @@ FUNCTIONS = {
     "calculate": ["get_believe", "line2point_distance_3D", "line2line_distance_3D"],
     "matching": ["back_project_ray", "epipolar_distance", "epipolar_affinity", "epipolar_affinity_parallel",
                  "Greedy_matching", "BIP_matching"],
-    "construction": ["SVD_pose_kernel", "SVD_pose_kernel_jf", "SVD_pose_kernel_parallel"],
+    "construction": ["SVD_pose_kernel", "SVD_pose_kernel_jf", "SVD_pose_kernel_parallel", "top_down_pose_kernel"],
 }
 METHODS = {
     ("hypothesis", "Hypothesis"): ["__init__", "size", "merge", "calculate_cost", "get_3dpose_jf"],
     ("IterativeTracker", "IterativeTracker"): ["__init__", "track_restart", "tracking"],
+    ("OneEuroFilter", "OneEuroFilter"): ["__init__", "__call__"],
 }
 
 
