@@ -52,4 +52,7 @@ def Greedy_matching(cameras, pose_mat=None, affinity_mat=None, costs=None, next_
 
 
 def BIP_matching(model, cameras, dimGroup, pose_mat=None, num_joints=17, threshold=40):
-    raise NotImplementedError("BIP_matching has no caller on the Iterative path (SURVEY.md section 2, row 11)")
+    raise NotImplementedError(
+        "BIP_matching has no caller on the Iterative path (SURVEY.md section 2, row 11), and its solver "
+        "(tracking/binary_integer_programming.py:188-202) needs cvxopt, which is not available to pin parity against; "
+        "the all-pairs affinity it starts from is epipolar_affinity (pam_epipolar_allpairs)")
