@@ -317,6 +317,14 @@ int pam_eval_panoptic_match(pam_handle* h, const int32_t* d_out_count, const flo
 int pam_one_euro(pam_handle* h, const double* d_x, int32_t n, double freq, double mincutoff, double beta, double dcutoff,
                  double* d_state, double* d_out, void* stream);
 
+/* Kalman smoother bank (tracking/KalmanFilter.py:4-65: cv2.KalmanFilter(9, 3) per 3-D joint, constant acceleration,
+ * float32).  d_state [n][90] f32 = state vector (9) + error covariance (81); initialise the first three state entries
+ * with the joint and the rest with zeros (KalmanFilter.__init__).  One call = the reference's predict(pt3d): correct with
+ * d_meas_or_null [n][3] f64 where d_has_meas_or_null [n] (null = all) is set, then predict; d_out [n][3] = predicted
+ * positions.  Agrees with OpenCV to float32 rounding (it inverts the 3 x 3 innovation covariance by SVD). */
+int pam_kalman9(pam_handle* h, const double* d_meas_or_null, const uint8_t* d_has_meas_or_null, int32_t n, double hz,
+                float* d_state, double* d_out, void* stream);
+
 /* top_down_pose_kernel (utils/construction.py:9-31): every camera pair triangulates all joints from its two views
  * (cv2.triangulatePoints' 4 x 4 system); the pair whose pose reprojects best into all cameras wins.
  * d_poses2d [batch][n_views][J][2] f64 (x, y), d_cam [batch][n_views] i32 -> d_pose3d [batch][J][3] f64,

@@ -101,6 +101,7 @@ _PROTOTYPES = [
     ("pam_eval_panoptic_match", C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     ("pam_ray_distance", C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, _P, _P, _P]),
     ("pam_one_euro", C.c_int, [_P, _P, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P, _P]),
+    ("pam_kalman9", C.c_int, [_P, _P, _P, C.c_int32, C.c_double, _P, _P, _P]),
     ("pam_top_down", C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     ("pam_camera_ingest", C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
 ]

@@ -865,4 +865,95 @@ k_top_down(const float* __restrict__ P, const double* __restrict__ poses2d, cons
     }
 }
 
+// Kalman smoother bank (tracking/KalmanFilter.py:4-65: cv2.KalmanFilter(9, 3), constant-acceleration model per 3-D
+// joint, float32).  One thread per filter; state [n][90] f32 = statePre/Post (9) + error covariance (81).
+// step = the reference's predict(pt3d): correct(measurement) when one is given, then predict(); returns the predicted
+// position.  Products are accumulated in double and rounded to float32 per matrix like OpenCV's float gemm; the 3 x 3
+// innovation covariance is inverted directly (OpenCV: SVD solve), so results agree to float32 rounding, not bit for bit.
+struct Kalman9 {
+    float v, a, q, r;      // dt, dt^2 / 2, process noise (0.007), measurement noise (0.1)
+};
+__device__ __forceinline__ float kal_A(const Kalman9& k, int i, int j) {      // transition matrix, row i, column j
+    if (i == j) return 1.f;
+    if (j == i + 3) return k.v;
+    if (j == i + 6) return k.a;
+    return 0.f;
+}
+__global__ void k_kalman9(int n, Kalman9 kp, const double* __restrict__ meas /* [n][3] or null */,
+                          const unsigned char* __restrict__ has_meas /* [n] or null = all */, float* __restrict__ state,
+                          double* __restrict__ out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    float* x = state + (int64_t)f * 90;
+    float* P = x + 9;
+    if (meas && (!has_meas || has_meas[f])) {
+        // correct(): H = first three rows of A (tracking/KalmanFilter.py:13-17)
+        float T2[3][9], S[3][3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 9; ++j) {
+                double s = 0.0;
+                for (int k = 0; k < 9; ++k) s += (double)kal_A(kp, i, k) * (double)P[k * 9 + j];
+                T2[i][j] = (float)s;
+            }
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0.0;
+                for (int k = 0; k < 9; ++k) s += (double)T2[i][k] * (double)kal_A(kp, j, k);
+                S[i][j] = (float)(s + (i == j ? (double)kp.r : 0.0));
+            }
+        // temp4 = S^-1 T2  (3 x 9);  gain = temp4^T
+        double Sd[9], Si[9];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Sd[i * 3 + j] = (double)S[i][j];
+        inv33<double>(Sd, Si);
+        float G[9][3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 9; ++j) {
+                double s = 0.0;
+                for (int k = 0; k < 3; ++k) s += Si[i * 3 + k] * (double)T2[k][j];
+                G[j][i] = (float)s;
+            }
+        float y[3];
+        for (int i = 0; i < 3; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < 9; ++k) s += (double)kal_A(kp, i, k) * (double)x[k];
+            y[i] = (float)((double)(float)meas[(int64_t)f * 3 + i] - s);
+        }
+        float xn[9], Pn[81];
+        for (int i = 0; i < 9; ++i) {
+            double s = (double)x[i];
+            for (int k = 0; k < 3; ++k) s += (double)G[i][k] * (double)y[k];
+            xn[i] = (float)s;
+        }
+        for (int i = 0; i < 9; ++i)
+            for (int j = 0; j < 9; ++j) {
+                double s = (double)P[i * 9 + j];
+                for (int k = 0; k < 3; ++k) s -= (double)G[i][k] * (double)T2[k][j];
+                Pn[i * 9 + j] = (float)s;
+            }
+        for (int i = 0; i < 9; ++i) x[i] = xn[i];
+        for (int i = 0; i < 81; ++i) P[i] = Pn[i];
+    }
+    // predict(): x = A x;  P = A P A^T + Q
+    float xp[9], T1[81];
+    for (int i = 0; i < 9; ++i) {
+        double s = 0.0;
+        for (int k = 0; k < 9; ++k) s += (double)kal_A(kp, i, k) * (double)x[k];
+        xp[i] = (float)s;
+    }
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j < 9; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 9; ++k) s += (double)kal_A(kp, i, k) * (double)P[k * 9 + j];
+            T1[i * 9 + j] = (float)s;
+        }
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j < 9; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 9; ++k) s += (double)T1[i * 9 + k] * (double)kal_A(kp, j, k);
+            P[i * 9 + j] = (float)(s + (i == j ? (double)kp.q : 0.0));
+        }
+    for (int i = 0; i < 9; ++i) x[i] = xp[i];
+    out[(int64_t)f * 3] = (double)xp[0]; out[(int64_t)f * 3 + 1] = (double)xp[1]; out[(int64_t)f * 3 + 2] = (double)xp[2];
+}
+
 }  // namespace pam

@@ -52,7 +52,15 @@ def Greedy_matching(cameras, pose_mat=None, affinity_mat=None, costs=None, next_
 
 
 def BIP_matching(model, cameras, dimGroup, pose_mat=None, num_joints=17, threshold=40):
-    raise NotImplementedError(
-        "BIP_matching has no caller on the Iterative path (SURVEY.md section 2, row 11), and its solver "
-        "(tracking/binary_integer_programming.py:188-202) needs cvxopt, which is not available to pin parity against; "
-        "the all-pairs affinity it starts from is epipolar_affinity (pam_epipolar_allpairs)")
+    """All-detections clustering front end (src/utils/matching.py:234-241): camera index per detection from the
+    ``dimGroup`` offsets, all-pairs epipolar affinity on the device (``pam_epipolar_allpairs``, float32 like the
+    reference), ``1 - affinity / threshold``, and the CALLER's solver object decides the clusters
+    (``model.solve``; the reference instantiates ``GLPKSolver`` from tracking/binary_integer_programming.py, which needs
+    cvxopt and a pre-1.11 scipy simplex -- neither is part of this package).  -> (matched_list, sub_imgid2cam)."""
+    sub_imgid2cam = np.zeros(dimGroup[-1] if dimGroup[-1] - 1 >= 0 else 0, dtype=np.int32)
+    for idx, i in enumerate(range(len(dimGroup) - 1)):
+        sub_imgid2cam[dimGroup[i]:dimGroup[i + 1]] = idx
+    affinity_mat, _ = epipolar_affinity(cameras, sub_imgid2cam, pose_mat, num_joints)
+    affinity_mat = 1 - affinity_mat / threshold
+    matched_list = model.solve(affinity_mat.astype(np.double))
+    return matched_list, sub_imgid2cam

@@ -324,3 +324,20 @@ def one_euro(x, state, freq, mincutoff, beta, dcutoff, device: int = 0):
                           float(dcutoff), C.c_void_p(state.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(st))
     _check(lib, h, rc)
     return out.cpu().numpy()
+
+
+def kalman9(meas, state, hz=25.0, has_meas=None, device: int = 0):
+    """One step of a bank of the reference's Kalman smoothers (src/tracking/KalmanFilter.py:52-65, ``predict(pt3d)``):
+    ``meas`` (n, 3) float64 or None (predict only), ``state`` a CUDA tensor (n, 90) float32 updated in place
+    -> predicted positions (n, 3) as numpy."""
+    torch = _torch()
+    lib, h = _bare_handle(device)
+    n = state.shape[0]
+    md = None if meas is None else torch.as_tensor(np.asarray(meas, dtype=np.float64).reshape(n, 3), device=f"cuda:{device}")
+    hm = None if has_meas is None else torch.as_tensor(np.asarray(has_meas, dtype=np.uint8).reshape(n), device=f"cuda:{device}")
+    out = torch.empty((n, 3), dtype=torch.float64, device=f"cuda:{device}")
+    st = torch.cuda.current_stream(device).cuda_stream
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    _check(lib, h, lib.pam_kalman9(h, p(md), p(hm), n, float(hz), p(state), p(out), C.c_void_p(st)))
+    return out.cpu().numpy()
+

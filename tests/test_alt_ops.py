@@ -100,3 +100,94 @@ def test_top_down_pose_kernel_matches_oracle(shape):
             k += 1
     assert tuple(pair) == min(((i, j) for i in range(len(pm)) for j in range(i + 1, len(pm))),
                               key=lambda ij: err[[(a, b) for a in range(len(pm)) for b in range(a + 1, len(pm))].index(ij)])
+
+
+class _RecordingSolver:
+    """Stands in for the caller's solver object: keeps the matrix it is handed and clusters by a plain threshold."""
+
+    def solve(self, affinity_matrix, rtn_matrix=False):
+        self.seen = np.array(affinity_matrix)
+        n = len(affinity_matrix)
+        labels = list(range(n))
+        for i in range(n):
+            for j in range(i + 1, n):
+                if affinity_matrix[i, j] > 0.5:
+                    labels[j] = labels[i]
+        return [[k for k in range(n) if labels[k] == lab] for lab in sorted(set(labels))]
+
+
+@pytest.mark.gpu
+def test_bip_matching_front_end_matches_oracle():
+    """BIP_matching (src/utils/matching.py:234-241): the matrix handed to the caller's solver and the camera index per
+    detection; the solver itself is the caller's object."""
+    from oracle import generic
+    D = util.load_dropin()
+    st = synth.make_stream("shelf17", 2, 2, miss_prob=0.1)
+    cams = camera.GetCameraParameters(st.rig)
+    ocams = generic.build_cameras(st.rig["P"], st.rig["K"], st.rig["RT"])
+    V = st.shape.V
+    poses = np.concatenate([st.dets[1, c, :st.counts[1, c]].astype(np.float64) for c in range(V)])
+    dim_group = np.concatenate([[0], np.cumsum(st.counts[1])]).astype(int)
+    model = _RecordingSolver()
+    matched, cam_of = D.matching.BIP_matching(model, cams, dim_group, poses, 17, 40)
+    ref_cam = np.concatenate([np.full(st.counts[1, c], c) for c in range(V)]).astype(np.int32)
+    assert cam_of.dtype == np.int32 and np.array_equal(cam_of, ref_cam)
+    ref_aff, _ = generic.epipolar_affinity(ocams, ref_cam, poses, 17)
+    ref_mat = (1 - ref_aff / 40).astype(np.double)
+    assert model.seen.dtype == np.float64 and np.allclose(model.seen, ref_mat, rtol=1e-5, atol=1e-5)
+    assert matched == _RecordingSolver().solve(ref_mat)
+    # detections of one person end up in one cluster (the same person's poses are epipolar-consistent)
+    person = np.concatenate([st.person_of_det[1, c, :st.counts[1, c]] for c in range(V)])
+    for cl in matched:
+        assert len(set(person[cl].tolist())) == 1
+
+
+@pytest.mark.gpu
+def test_kalman_bank_matches_cv2_kalman_filter():
+    """KalmanFilter (src/tracking/KalmanFilter.py:4-65): the reference's class is cv2.KalmanFilter(9, 3) with fixed
+    matrices; the device bank must follow it through corrections, missing measurements and pure predictions to float32
+    rounding (OpenCV inverts the innovation covariance by SVD, the kernel directly)."""
+    import cv2
+    D = util.load_dropin()
+
+    def reference_filter(pt3d, Hz=25):            # the constructor of KalmanFilter.py:5-50, same cv2 object
+        dt = 1.0 / Hz
+        v, a = dt, 0.5 * (dt ** 2)
+        k = cv2.KalmanFilter(9, 3, 0)
+        A = np.eye(9, dtype=np.float32)
+        for i in range(6):
+            A[i, i + 3] = v
+        for i in range(3):
+            A[i, i + 6] = a
+        k.transitionMatrix = A
+        k.measurementMatrix = A[:3].copy()
+        k.processNoiseCov = np.eye(9, dtype=np.float32) * 0.007
+        k.measurementNoiseCov = np.eye(3, dtype=np.float32) * 0.1
+        k.statePre = np.array([[np.float32(pt3d[0])], [np.float32(pt3d[1])], [np.float32(pt3d[2])]] + [[np.float32(0.)]] * 6)
+        return k
+
+    def reference_predict(k, pt3d=None):          # KalmanFilter.py:52-65
+        if pt3d is not None:
+            k.correct(np.array([[np.float32(pt3d[0])], [np.float32(pt3d[1])], [np.float32(pt3d[2])]]))
+        return k.predict()[:3].flatten()
+
+    rng = np.random.default_rng(3)
+    J, T = 17, 80
+    t = np.arange(T)[:, None, None]
+    path = rng.uniform(-2, 2, (1, J, 3)) + 0.03 * t * rng.uniform(-1, 1, (1, J, 3)) + 0.002 * rng.normal(size=(T, J, 3))
+    bank = D.KalmanFilter.KalmanBank(path[0])
+    refs = [reference_filter(path[0, j]) for j in range(J)]
+    worst = 0.0
+    for k in range(T):
+        meas = None if k % 9 == 4 else path[k]                       # a frame without measurements: predict only
+        got = bank.predict(meas)
+        ref = np.array([reference_predict(refs[j], None if meas is None else meas[j]) for j in range(J)], dtype=np.float64)
+        err = np.abs(got - ref).max()
+        worst = max(worst, err)
+        assert err < 2e-4 * max(1.0, np.abs(ref).max()), (k, err)
+    one = D.KalmanFilter.KalmanFilter(path[0, 0])                    # the per-joint call surface
+    r1 = reference_filter(path[0, 0])
+    for k in range(10):
+        a, b = one.predict(path[k, 0]), reference_predict(r1, path[k, 0])
+        assert a.dtype == np.float32 and np.abs(a - b).max() < 2e-4
+    print(f"kalman bank: max deviation from cv2.KalmanFilter {worst:.2e} over {T} steps x {J} joints")

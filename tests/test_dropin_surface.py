@@ -21,6 +21,7 @@ METHODS = {
     ("hypothesis", "Hypothesis"): ["__init__", "size", "merge", "calculate_cost", "get_3dpose_jf"],
     ("IterativeTracker", "IterativeTracker"): ["__init__", "track_restart", "tracking"],
     ("OneEuroFilter", "OneEuroFilter"): ["__init__", "__call__"],
+    ("KalmanFilter", "KalmanFilter"): ["__init__", "predict"],
 }
 
 

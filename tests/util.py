@@ -142,7 +142,7 @@ def load_dropin():
     import types
     from pam_b200 import dropin
     here = _os.path.dirname(_os.path.abspath(dropin.__file__))   # not dropin.install(): keep sys.path clean
-    names = ["_pkg", "calculate", "matching", "construction", "hypothesis", "IterativeTracker", "OneEuroFilter"]
+    names = ["_pkg", "calculate", "matching", "construction", "hypothesis", "IterativeTracker", "OneEuroFilter", "KalmanFilter"]
     saved = {k: _sys.modules.get(k) for k in names}
     ns = types.SimpleNamespace()
     try:

@@ -9,7 +9,8 @@ T = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 S = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 rig, dets, counts, gt, streams = synth.make_batch(shape, S, T, miss_prob=0.1, outlier_prob=0.05)
 cams = camera.GetCameraParameters(rig)
-trk = tracker.SequenceTracker(cams, synth.tracker_params(shape), S, max_detections=dets.shape[3], max_tracks=8,
-                              arm_joints=synth.SHAPES[shape].arm_joints)
-out = trk.run(torch.from_numpy(dets).cuda(), torch.from_numpy(counts).cuda(), assoc=True)
-print("status", trk.check(), "reports", int(out["count"].sum()))
+trk = tracker.SequenceTracker(cams, synth.tracker_params(shape), S, max_detections=dets.shape[3],
+                              max_tracks=8 if synth.SHAPES[shape].P <= 4 else 16, arm_joints=synth.SHAPES[shape].arm_joints)
+out = trk.run(torch.from_numpy(dets).cuda(), torch.from_numpy(counts).cuda(), assoc=True, vlist=True, timing=True)
+print("launch", trk.launch_info())
+print("status", trk.check(strict=False), "reports", int(out["count"].sum()))
