@@ -42,6 +42,10 @@ struct GroupCtx {
     }
     __device__ __forceinline__ void atomic_inc(int* p) const { atomicAdd(p, 1); }
     __device__ __forceinline__ int atomic_inc_ret(int* p) const { return atomicAdd(p, 1); }
+    __device__ __forceinline__ void atomic_max_u64(unsigned long long* p, unsigned long long v) const { atomicMax(p, v); }
+    __device__ __forceinline__ void atomic_min(int* p, int v) const { atomicMin(p, v); }
+    __device__ __forceinline__ void atomic_min_u64(unsigned long long* p, unsigned long long v) const { atomicMin(p, v); }
+    __device__ __forceinline__ int enum_limit() const { return 1024 * G; }     // candidate assignments worth enumerating: <= 32 per thread
     __device__ __forceinline__ long long clock() const { return clock64(); }
 };
 

@@ -108,6 +108,10 @@ struct FrameScalars {
     int hyp_n;
     int warned;            // something was dropped this frame
     int n_surv;            // two-pass affinity: (track, camera, detection) items that survived the probe
+    int unsure;            // sign-only affinity: some joint fell inside the guard band, the frame is evaluated exactly
+    int bf_k;              // enumerated assignment: index of the best candidate
+    unsigned long long bf_best;   //                  and the bit pattern of its total affinity
+    unsigned long long bf_sig_lo, bf_sig_hi;   //     smallest / largest signature among the candidates that reach it
 };
 
 // One usable view of a track for the current frame: where its (v, u, conf) triples live (the staged
@@ -153,12 +157,13 @@ inline int caps_class(int V, int D, int J, int T) {
 }
 
 // camera constants of the rig, widened to double, shared by every sequence of a CTA
+// (every matrix starts on a 16-byte boundary, so that its rows are fetched with 128-bit shared-memory loads)
 template <class K>
-struct CamShared {
+struct alignas(16) CamShared {
     double P[K::V][12];
-    double RK[K::V][9];
-    double pos[K::V][3];
-    double F[K::V][K::V][9];
+    double RK[K::V][10];
+    double pos[K::V][4];
+    double F[K::V][K::V][10];
 };
 
 // The fixed part of one sequence's working set (shared memory on the device).
@@ -173,6 +178,7 @@ struct SeqShared {
     double believe[K::V][K::D];              // mean confidence of every detection
     double inv_denom[K::T];                  // 1 / (alpha2d * dt)
     double inv_decay[K::T];                  // 1 / exp(lambda_a * dt)
+    double thr2_lo[K::T], thr2_hi[K::T];     // (alpha2d dt)^2 (1 -+ 2^-24): a joint is surely inside / surely outside
     ViewSrc vsrc[K::T][K::V];                // gathered views per track, dict order
     int dt[K::T];
     int fail[K::T];                          // joints left with < 2 views
@@ -311,7 +317,11 @@ struct HostCtx {
     inline void phase_sync() const {}
     inline void atomic_inc(int* p) const { *p += 1; }
     inline int atomic_inc_ret(int* p) const { return (*p)++; }
+    inline void atomic_max_u64(unsigned long long* p, unsigned long long v) const { if (v > *p) *p = v; }
+    inline void atomic_min_u64(unsigned long long* p, unsigned long long v) const { if (v < *p) *p = v; }
+    inline void atomic_min(int* p, int v) const { if (v < *p) *p = v; }
     inline long long clock() const { return 0; }
+    inline int enum_limit() const { return 1024; }      // as a one-warp group on the device
     static bool kTwoPassAffinity;            // set by the harness (PAM_HOSTEMU_TWOPASS=1)
 };
 struct NoHook {
@@ -356,6 +366,7 @@ PAM_HD void load_cameras(int t, int nt, const DevCfg& c, CamShared<K>* cam, cons
     PAM_NOUNROLL for (int i = t; i < V * 9; i += nt) cam->RK[i / 9][i % 9] = (double)cc.RKinv[i];
     PAM_NOUNROLL for (int i = t; i < V * 3; i += nt) cam->pos[i / 3][i % 3] = cc.pos[i];
     PAM_NOUNROLL for (int i = t; i < V * V * 9; i += nt) cam->F[i / (9 * V)][(i / 9) % V][i % 9] = (double)cc.F[i];
+    PAM_NOUNROLL for (int i = t; i < V * V; i += nt) cam->F[i / V][i % V][9] = 0.0;      // padding, never read
 }
 
 template <class Ctx, class K>
@@ -576,6 +587,155 @@ PAM_HD bool track_reported(const DevCfg& c, const Seq<K>& sq, int i) {
 // `hook.dets_released()` is called by every thread once the staged detections are no longer needed
 // (single-buffered launches start the copy of the next frame there).
 // The caller must synchronise the group after frame_step returns.
+// index of the k-th set bit of m (k < popcount(m))
+PAM_HD int nth_set_bit(uint32_t m, int k) {
+    PAM_NOUNROLL for (; k > 0; --k) m &= m - 1u;
+    return ctz32(m);
+}
+
+// One camera's assignment problem (IterativeTracker.py:150-160: scipy's linear_sum_assignment on -affinity, pairs with
+// affinity <= 0 dropped afterwards), solved by the whole thread group when it is small.  Entries that are not
+// positive contribute nothing and any matching of positive entries extends to a complete assignment, so the optimum
+// is the maximum-weight matching of the positive entries.  Pairs already fixed by the quick test are isolated; the
+// rest -- r rows and c columns that hold a positive entry -- is enumerated: every injective map of the shorter side
+// into the longer one is a candidate (p! / (p - o)! of them), its total is summed in index order of the shorter side
+// (candidates with the same positive pairs have bit-identical totals), the threads keep their best candidate and two
+// shared-memory atomics pick the largest total.  The solver of the reference reaches the same optimum unless two
+// different matchings tie to within rounding.  Returns false (nothing written) when the problem has more than `limit`
+// candidates or when two different matchings tie exactly: the caller then runs the general solver.
+template <class Ctx, class K>
+PAM_HD bool assign_enumerated(Ctx& ctx, SeqShared<K>& sh, int cam, int n, int mm, int limit) {
+    const double (*A)[K::D] = sh.aff[cam];
+    FrameScalars& fs = sh.fs;
+    uint32_t rows = 0u, cols = 0u;
+    PAM_NOUNROLL for (int i = 0; i < n; ++i) {
+        if (sh.t2d(cam, i) >= 0) continue;                      // fixed by the quick test
+        PAM_NOUNROLL for (int d = 0; d < mm; ++d)
+            if (A[i][d] > 0.0) { rows |= 1u << i; cols |= 1u << d; }
+    }
+    const int r = popcount32(rows), cc = popcount32(cols);
+    const bool by_rows = r <= cc;                               // the shorter side is mapped into the longer one
+    const int o = by_rows ? r : cc, p = by_rows ? cc : r;
+    const uint32_t outer = by_rows ? rows : cols, pool = by_rows ? cols : rows;
+    int P = 1;
+    PAM_NOUNROLL for (int q = 0; q < o; ++q) {
+        P *= p - q;
+        if (P > limit) return false;                            // uniform: every thread sees the same matrix
+    }
+    ctx.sync();                                                 // the previous camera's verdict has been read by everyone
+    if (ctx.tid() == 0) { fs.bf_best = 0ull; fs.bf_k = P; fs.bf_sig_lo = ~0ull; fs.bf_sig_hi = 0ull; }
+    ctx.sync();
+    // total of candidate k and a signature of its positive pairs (order-independent 64-bit mix)
+    auto total = [&](int k, unsigned long long& sig) {
+        uint32_t avail = pool, left = outer;
+        double sum = 0.0;
+        sig = 0ull;
+        PAM_NOUNROLL for (int q = 0; q < o; ++q) {
+            const int base = p - q, digit = k % base;
+            k /= base;
+            const int a = ctz32(left), b = nth_set_bit(avail, digit);
+            left &= left - 1u;
+            avail &= ~(1u << b);
+            const double x = by_rows ? A[a][b] : A[b][a];
+            sum += x;
+            if (x > 0.0) {
+                unsigned long long z = (unsigned long long)((by_rows ? a : b) * 64 + (by_rows ? b : a) + 1) * 0x9E3779B97F4A7C15ull;
+                z ^= z >> 31; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 29;
+                sig ^= z;
+            }
+        }
+        return sum;
+    };
+    auto bits_of = [](double x) { unsigned long long b; memcpy(&b, &x, 8); return b; };   // non-negative: ordered like x
+    double best = -1.0;
+    PAM_FOR(k, P) {
+        unsigned long long sig;
+        const double t = total(k, sig);
+        if (t > best) best = t;
+    }
+    if (best >= 0.0) ctx.atomic_max_u64(&fs.bf_best, bits_of(best));
+    ctx.sync();
+    // the candidates that reach the maximum: lowest index, and whether they all hold the same positive pairs
+    if (best >= 0.0 && bits_of(best) == fs.bf_best) {
+        PAM_FOR(k, P) {
+            unsigned long long sig;
+            if (bits_of(total(k, sig)) != fs.bf_best) continue;
+            ctx.atomic_min(&fs.bf_k, k);
+            ctx.atomic_min_u64(&fs.bf_sig_lo, sig);
+            ctx.atomic_max_u64(&fs.bf_sig_hi, sig);
+        }
+    }
+    ctx.sync();
+    // two different matchings with the same total (duplicated detections or tracks): which one the reference's solver
+    // returns depends on its pivoting order, so that solver decides
+    if (fs.bf_sig_lo != fs.bf_sig_hi) return false;
+    if (ctx.tid() == 0) {
+        int k = fs.bf_k;
+        uint32_t avail = pool, left = outer;
+        PAM_NOUNROLL for (int q = 0; q < o; ++q) {
+            const int base = p - q, digit = k % base;
+            k /= base;
+            const int a = ctz32(left), b = nth_set_bit(avail, digit);
+            left &= left - 1u;
+            avail &= ~(1u << b);
+            const int i = by_rows ? a : b, d = by_rows ? b : a;
+            if (A[i][d] > 0.0) { sh.t2d(cam, i) = (signed char)d; sh.d2t(cam, d) = (signed char)i; }
+        }
+    }
+    return true;
+}
+
+// The same problem when, besides the pairs fixed by the quick test, at most two tracks and two detections -- or one
+// track / one detection against several -- hold positive entries: the rule when two people cross.  One thread
+// decides it in closed form (every camera in parallel).  Returns false when the camera needs more than that, or when
+// the two alternatives tie exactly.
+template <class K>
+PAM_HD bool assign_closed_form(SeqShared<K>& sh, int cam, int n, int mm) {
+    const double (*A)[K::D] = sh.aff[cam];
+    uint32_t rows = 0u, cols = 0u;
+    PAM_NOUNROLL for (int i = 0; i < n; ++i) {
+        if (sh.t2d(cam, i) >= 0) continue;
+        PAM_NOUNROLL for (int d = 0; d < mm; ++d)
+            if (A[i][d] > 0.0) { rows |= 1u << i; cols |= 1u << d; }
+    }
+    const int r = popcount32(rows), cc = popcount32(cols);
+    auto take = [&](int i, int d) {
+        if (A[i][d] > 0.0) { sh.t2d(cam, i) = (signed char)d; sh.d2t(cam, d) = (signed char)i; }
+    };
+    if (r == 1 || cc == 1) {
+        // one track with several candidate detections, or several tracks after one detection: the largest entry
+        const bool one_row = r == 1;
+        const int fixed = ctz32(one_row ? rows : cols);
+        uint32_t rest = one_row ? cols : rows;
+        double best = 0.0;
+        int arg = -1, ties = 0;
+        PAM_NOUNROLL for (; rest; rest &= rest - 1u) {
+            const int x = ctz32(rest);
+            const double a = one_row ? A[fixed][x] : A[x][fixed];
+            if (a > best) { best = a; arg = x; ties = 0; }
+            else if (a == best) ++ties;
+        }
+        if (ties || arg < 0) return false;
+        if (one_row) take(fixed, arg); else take(arg, fixed);
+        return true;
+    }
+    if (r == 2 && cc == 2) {
+        const int i0 = ctz32(rows), i1 = ctz32(rows & (rows - 1u)), d0 = ctz32(cols), d1 = ctz32(cols & (cols - 1u));
+        const double straight = A[i0][d0] + A[i1][d1], crossed = A[i0][d1] + A[i1][d0];
+        if (straight == crossed) return false;
+        if (straight > crossed) { take(i0, d0); take(i1, d1); }
+        else { take(i0, d1); take(i1, d0); }
+        return true;
+    }
+    return false;
+}
+
+// relative half-width of the guard band of the sign-only affinity test (phase 2); tests widen it to drive
+// joints through the exact fallback
+#if !defined(PAM_SIGN_BAND)
+#define PAM_SIGN_BAND 5.9604644775390625e-08     /* 2^-24 */
+#endif
+
 template <class Ctx, class K, class Hook>
 PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, const float* dets /* [V][D][J][3] */,
                        const int* counts /* [V] */, const FrameOut& out, const float* gin, int gin_frame0, Hook& hook) {
@@ -611,10 +771,19 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
             sh.inv_denom[i] = 1.0 / (c.alpha2d * (double)dt);
             sh.inv_decay[i] = 1.0 / exp(c.lambda_a * (double)dt);
         }
+        {
+            // sign-only affinity (phase 2): valid when dt > 0 and the decay factor is an ordinary positive number, so
+            // that "more than min_valid joints with c > 0" is the same as "affinity > 0"; otherwise lo > hi sends every
+            // joint of this track through the exact evaluation
+            const double th = c.alpha2d * (double)dt, th2 = th * th;
+            const bool plain = dt > 0 && th > 0.0 && th2 < 1e300 && sh.inv_decay[i] > 1e-150 && sh.inv_decay[i] < 1e150;
+            sh.thr2_lo[i] = plain ? th2 * (1.0 - PAM_SIGN_BAND) : -1.0;
+            sh.thr2_hi[i] = plain ? th2 * (1.0 + PAM_SIGN_BAND) : HUGE_VAL;
+        }
         sh.fail[i] = 0;
         sh.new_view[i] = 0;
     }
-    if (ctx.tid() == ctx.nthreads() - 1) { fs.any_conflict = 0; fs.any_deleted = 0; fs.n_surv = 0; }
+    if (ctx.tid() == ctx.nthreads() - 1) { fs.any_conflict = 0; fs.any_deleted = 0; fs.n_surv = 0; fs.unsure = 0; }
     PAM_FOR_REV(cc, V) {
         int mm = counts[cc];
         if (mm > D || mm < 0) { hdr.warn |= WARN_DET_OVERFLOW; fs.warned = 1; mm = (mm < 0) ? 0 : D; }
@@ -657,6 +826,39 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
         if (a > 0.0) PAM_NOTE(MG_ASSIGN, a);
         return a;
     };
+#if !defined(PAM_MARGIN)
+    // Sign-only evaluation.  Phase 3 needs the VALUE of an affinity only in a camera whose positive entries do not
+    // already form a matching; everywhere else it needs the sign, and affinity > 0 <=> more than min_valid joints
+    // have c > 0 <=> |x_proj - x_det| < alpha2d dt.  That comparison is made without the division and the square
+    // root, on |n - q w|^2 against (alpha2d dt)^2 w^2 with a relative guard band of 2^-24 on either side (the two
+    // forms differ by ~1e-13 relative at most).  A joint inside the band -- or any joint of a track whose dt or
+    // decay is not an ordinary number -- makes the whole frame fall back to the exact expression.  Otherwise the entry
+    // holds 1 (positive) or 0; the cameras that need values get them in phase 3.
+    auto count_joints = [&](int i, int cam, int d, int j0, int j1, int& cnt) {
+        const double* X = g.hist + (int64_t)(hdr.order[i] * PAM_HIST + sh.last[i]) * J3;
+        const double* P = sq.Pc(cam);
+        const double p0 = P[0], p1 = P[1], p2 = P[2], p3 = P[3], p4 = P[4], p5 = P[5], p6 = P[6], p7 = P[7];
+        const double p8 = P[8], p9 = P[9], p10 = P[10], p11 = P[11];
+        const float* q = dets + (int64_t)(cam * D + d) * J3;
+        const double lo = sh.thr2_lo[i], hi = sh.thr2_hi[i];
+        uint32_t unsure = 0u;                        // joints inside the guard band (J <= 32)
+        PAM_UNROLL_N(Ctx::kAffinityUnroll) for (int j = j0; j < j1; ++j) {      // straight-line body: the joints interleave
+            const double x = X[j * 3], y = X[j * 3 + 1], z = X[j * 3 + 2];
+            const double w = p8 * x + p9 * y + p10 * z + p11;
+            const double ev = (p4 * x + p5 * y + p6 * z + p7) - (double)q[j * 3 + 0] * w;
+            const double eu = (p0 * x + p1 * y + p2 * z + p3) - (double)q[j * 3 + 1] * w;
+            const double e2 = ev * ev + eu * eu, w2 = w * w;
+            const bool inside = e2 < lo * w2, outside = e2 > hi * w2;
+            cnt += inside ? 1 : 0;
+            unsure |= (inside || outside) ? 0u : (1u << j);
+        }
+        if (unsure) fs.unsure = 1;                   // practically never
+    };
+    constexpr bool kSignOnly = true;
+#else
+    auto count_joints = [&](int, int, int, int, int, int&) {};
+    constexpr bool kSignOnly = false;     // the margin build looks at every c
+#endif
     if (Ctx::kTwoPassAffinity && c.aff_probe > 0 && V * n * D > ctx.nthreads()) {      // pays from two sweeps on
         // Throughput launches.  Most (track, detection) pairs belong to different people: after the first
         // `aff_probe` joints such a pair can no longer collect more than min_valid joints with c > 0, so its
@@ -669,7 +871,8 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
             if (d >= sh.m[cam]) continue;
             double sum = 0.0;
             int cnt = 0;
-            affinity_joints(i, cam, d, 0, JA, sum, cnt);
+            if (kSignOnly) count_joints(i, cam, d, 0, JA, cnt);
+            else affinity_joints(i, cam, d, 0, JA, sum, cnt);
             if (cnt + (J - JA) <= c.min_valid) { sh.aff[cam][i][d] = 0.0; continue; }
             sh.aff[cam][i][d] = sum;
             sh.pcnt[cam][i][d] = (unsigned char)cnt;
@@ -681,8 +884,13 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
             const int i = fast_div(it, c.inv_VD), rem = it - i * (V * D), cam = fast_div(rem, c.inv_D), d = rem - cam * D;
             double sum = sh.aff[cam][i][d];
             int cnt = sh.pcnt[cam][i][d];
-            affinity_joints(i, cam, d, JA, J, sum, cnt);
-            sh.aff[cam][i][d] = affinity_value(i, sum, cnt);
+            if (kSignOnly) {
+                count_joints(i, cam, d, JA, J, cnt);
+                sh.aff[cam][i][d] = (cnt > c.min_valid) ? 1.0 : 0.0;
+            } else {
+                affinity_joints(i, cam, d, JA, J, sum, cnt);
+                sh.aff[cam][i][d] = affinity_value(i, sum, cnt);
+            }
         }
     } else {
         PAM_FOR(it, V * n * D) {
@@ -690,11 +898,70 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
             if (d >= sh.m[cam]) continue;
             double sum = 0.0;
             int cnt = 0;
-            affinity_joints(i, cam, d, 0, J, sum, cnt);
-            sh.aff[cam][i][d] = affinity_value(i, sum, cnt);
+            if (kSignOnly) {
+                count_joints(i, cam, d, 0, J, cnt);
+                sh.aff[cam][i][d] = (cnt > c.min_valid) ? 1.0 : 0.0;
+            } else {
+                affinity_joints(i, cam, d, 0, J, sum, cnt);
+                sh.aff[cam][i][d] = affinity_value(i, sum, cnt);
+            }
         }
     }
     ctx.phase_sync();
+    // every affinity of the frame (all = true), or the positive entries of the cameras that need the solver, by the
+    // exact expression
+    auto exact_affinities = [&](bool all) {
+        if (!all) {
+            // few entries, on the critical path of the CTA's convoy: one joint per thread, the terms parked in the
+            // (idle) raw-pose buffer, then summed in joint order by one thread per entry -- the same additions in the
+            // same order as the loop below
+            if (ctx.tid() == 0) fs.n_surv = 0;
+            ctx.sync();
+            PAM_FOR(it, V * n * D) {
+                const int i = fast_div(it, c.inv_VD), rem = it - i * (V * D), cam = fast_div(rem, c.inv_D), d = rem - cam * D;
+                if (d < sh.m[cam] && sh.conflict[cam] && sh.aff[cam][i][d] > 0.0)
+                    sh.surv[ctx.atomic_inc_ret(&fs.n_surv)] = (unsigned short)it;
+            }
+            ctx.sync();
+            const int E = fs.n_surv;
+            if (E <= c.max_trk * 3) {                          // the buffer holds max_trk * J * 3 doubles
+                double* const term = sq.raw_;
+                PAM_FOR(x, E * J) {
+                    const int e = fast_div(x, c.inv_J), j = x - e * J, it = sh.surv[e];
+                    const int i = fast_div(it, c.inv_VD), rem = it - i * (V * D), cam = fast_div(rem, c.inv_D), d = rem - cam * D;
+                    double cj = 0.0;
+                    int one = 0;
+                    affinity_joints(i, cam, d, j, j + 1, cj, one);
+                    term[x] = cj;                              // c_j where it is positive, else 0
+                }
+                ctx.sync();
+                PAM_FOR(e, E) {
+                    const int it = sh.surv[e];
+                    const int i = fast_div(it, c.inv_VD), rem = it - i * (V * D), cam = fast_div(rem, c.inv_D), d = rem - cam * D;
+                    double sum = 0.0;
+                    int cnt = 0;
+                    PAM_NOUNROLL for (int j = 0; j < J; ++j) {
+                        const double cj = term[e * J + j];
+                        if (cj > 0.0) { sum += cj; ++cnt; }
+                    }
+                    sh.aff[cam][i][d] = affinity_value(i, sum, cnt);
+                }
+                ctx.sync();
+                return;
+            }
+        }
+        PAM_FOR(it, V * n * D) {
+            const int i = fast_div(it, c.inv_VD), rem = it - i * (V * D), cam = fast_div(rem, c.inv_D), d = rem - cam * D;
+            if (d >= sh.m[cam]) continue;
+            if (!all && (!sh.conflict[cam] || !(sh.aff[cam][i][d] > 0.0))) continue;
+            double sum = 0.0;
+            int cnt = 0;
+            affinity_joints(i, cam, d, 0, J, sum, cnt);
+            sh.aff[cam][i][d] = affinity_value(i, sum, cnt);
+        }
+        ctx.sync();
+    };
+    if (kSignOnly && fs.unsure) exact_affinities(true);      // uniform
 
     // ---- phase 3: one assignment problem per camera (IterativeTracker.py:150-160) ---------------
     // Only pairs with affinity > 0 are ever accepted.  When the positive entries of a camera's
@@ -732,8 +999,22 @@ PAM_HD void frame_step(Ctx& ctx, const DevCfg& c, const Seq<K>& sq, int frame, c
     }
     ctx.phase_sync();
     if (fs.any_conflict) {   // uniform
+        // the solver compares affinities: the positive entries of the flagged cameras get their values now
+        if (kSignOnly) exact_affinities(false);
+        // the quick test marked these cameras 1.  Two tracks and two detections that cross, or one against several, are
+        // decided in closed form by one thread per camera (-> 3); other small problems are enumerated by the whole
+        // group; the ones left for the general solver become 2
+        PAM_FOR(cam, V)
+            if (sh.conflict[cam] && assign_closed_form(sh, cam, n, sh.m[cam])) sh.conflict[cam] = 3;
+        ctx.sync();
+        PAM_NOUNROLL for (int cam = 0; cam < V; ++cam) {         // uniform
+            if (sh.conflict[cam] != 1) continue;
+            const bool done = assign_enumerated(ctx, sh, cam, n, sh.m[cam], ctx.enum_limit());
+            if (!done && ctx.tid() == 0) sh.conflict[cam] = 2;
+        }
+        ctx.sync();
         PAM_FOR(cam, V) {
-            if (!sh.conflict[cam]) continue;
+            if (sh.conflict[cam] != 2) continue;
             const int mm = sh.m[cam];
             const double (*A)[K::D] = sh.aff[cam];
             signed char* t2d = &sh.t2d(cam, 0);

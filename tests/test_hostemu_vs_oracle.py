@@ -27,6 +27,56 @@ def test_kernel_source_on_host_matches_oracle(shape, kw, T):
     assert out["count"].sum() > 0 and worst < 5e-4
 
 
+@pytest.mark.parametrize("shape,mult", [("shelf", 6.0), ("campus", 6.0), ("panoptic", 4.0)])
+@pytest.mark.parametrize("twopass", ["0", "1"])
+def test_wide_association_threshold_exercises_the_assignment_solver(shape, mult, twopass, monkeypatch):
+    """alpha2d several times the dataset value: most tracks see more than one candidate detection per camera, so a
+    large share of the frames goes through the full assignment solver.  The kernel only evaluates the SIGN of an
+    affinity until a camera needs the solver (then the values of its positive entries are filled in): decisions must
+    stay those of the reference, which computes every value (IterativeTracker.py:139-160)."""
+    monkeypatch.setenv("PAM_HOSTEMU_TWOPASS", twopass)
+    st = synth.make_stream(shape, 5, 160, miss_prob=0.1, outlier_prob=0.1)
+    p = synth.tracker_params(shape)
+    p["alpha2d"] = p["alpha2d"] * mult
+    cfg = util.stream_config(st, max_tracks=16 if shape == "panoptic" else 8, params=p)
+    out = util.run_hostemu([st], cfg)
+    assert out["status"].tolist() == [0]
+    oo, oa, _ = util.run_oracle(st, params=p)
+    assert util.compare_with_oracle(out, 0, st, oo, oa) < 5e-4
+
+
+def test_guard_band_fallback_of_the_sign_only_affinity():
+    """Host build with the guard band of the sign-only association test widened from 2^-24 to 0.6 (-DPAM_SIGN_BAND):
+    every joint between 0.63 and 1.26 of the threshold is then decided by the exact out-of-line expression.  Same
+    decisions as the oracle, i.e. the fallback agrees with the fast comparison wherever both apply."""
+    import ctypes as C
+    import os
+    import subprocess
+    import numpy as np
+    from pam_b200 import camera
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "hostemu", "_build", "libpam_hostemu_band.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-array-bounds",
+                           "-DPAM_SIGN_BAND=0.6", "-o", so, os.path.join(here, "hostemu", "hostemu.cpp")])
+    lib = C.CDLL(so)
+    st = synth.make_stream("shelf", 11, 150, miss_prob=0.1, outlier_prob=0.1)
+    p = synth.tracker_params("shelf")
+    p["alpha2d"] = 12.0                                    # detections scatter around the threshold
+    cfg = util.stream_config(st, max_tracks=32, params=p)          # short-lived tracks come and go: 8 slots overflow
+    P, RK, pos, F = camera.pack_cameras(camera.GetCameraParameters(st.rig))
+    dets, counts = np.ascontiguousarray(st.dets[None]), np.ascontiguousarray(st.counts[None])
+    out = util.alloc_outputs(cfg, 1, st.T)
+    status = np.zeros(1, np.int32)
+    rc = lib.hostemu_track_sequences(C.byref(cfg), util.ptr(P), util.ptr(RK), util.ptr(pos), util.ptr(F), 1, st.T, 0,
+                                     util.ptr(dets), util.ptr(counts), util.ptr(out["count"]), util.ptr(out["ids"]),
+                                     util.ptr(out["joints"]), util.ptr(out["nviews"]), util.ptr(out["assoc"]),
+                                     util.ptr(status), None, util.ptr(out["vlist"]))
+    assert rc == 0 and status[0] == 0
+    oo, oa, _ = util.run_oracle(st, params=p)
+    assert util.compare_with_oracle(out, 0, st, oo, oa) < 5e-4 and out["count"].sum() > 0
+
+
 def test_kernel_source_chunked_launches_carry_state():
     """Frames fed in several 'launches' (tracker state carried in the state buffer, stale views first read
     from the launch's own input, then from the persisted copies) give the result of a single launch."""

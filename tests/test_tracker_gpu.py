@@ -42,6 +42,31 @@ def test_device_path_matches_oracle(shape, kw, T):
     print(f"{shape}: max joint deviation {worst:.3e} m over {T} frames")
 
 
+@pytest.mark.parametrize("shape,mult,env", [("shelf", 6.0, ""), ("shelf", 6.0, "4:1:128"), ("shelf", 6.0, "1:8:128"),
+                                            ("campus", 6.0, "1:8:128"), ("panoptic", 4.0, "")])
+def test_wide_association_threshold_exercises_the_assignment_solver(shape, mult, env, monkeypatch):
+    """See tests/test_hostemu_vs_oracle.py: with alpha2d several times the dataset value most frames need the full
+    assignment solver, i.e. the values (not only the signs) of the affinities of the contested cameras."""
+    import torch
+    if env:
+        monkeypatch.setenv("PAM_TRACK_SHAPE", env)
+    S = 9 if env.startswith("1:") else 2
+    streams = [synth.make_stream(shape, 5 + k, 160, miss_prob=0.1, outlier_prob=0.1) for k in range(2)]
+    p = synth.tracker_params(shape)
+    p["alpha2d"] = p["alpha2d"] * mult
+    cams = camera.GetCameraParameters(streams[0].rig)
+    trk = tracker.SequenceTracker(cams, p, num_sequences=S, max_detections=streams[0].dets.shape[2],
+                                  max_tracks=16 if shape == "panoptic" else 8, arm_joints=streams[0].shape.arm_joints)
+    dets = torch.from_numpy(np.stack([streams[k % 2].dets for k in range(S)])).cuda()
+    counts = torch.from_numpy(np.stack([streams[k % 2].counts for k in range(S)])).cuda()
+    out = trk.run(dets, counts, nviews=True, assoc=True)
+    assert trk.check().tolist() == [0] * S
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    for s in (0, 1, S - 1):
+        oo, oa, _ = util.run_oracle(streams[s % 2], params=p)
+        util.compare_with_oracle(out, s, streams[s % 2], oo, oa)
+
+
 def _valid(out, key):
     """Mask the unused tail of the per-frame output slots (not written by the kernel)."""
     a = out[key]
