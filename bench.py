@@ -539,6 +539,8 @@ def main():
             counters[3] = pcp[:, :, 1].sum()
             counters[4] = (mpj[0] * 1e6).to(torch.int64)
             counters[5] = mpj[1].to(torch.int64)
+        if timed_events is not None:
+            timed_events[2].record(stream)
         pdist.reduce_counters(counters)
         if gathered is not None:
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -555,7 +557,7 @@ def main():
     launches0 = trk.launches
     sampler = ClockSampler(local_rank)
     sampler.start()
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    kev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(a.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pdist.barrier()
     torch.cuda.synchronize(dev)
@@ -569,7 +571,8 @@ def main():
     clocks = sampler.summary()
     launches = trk.launches - launches0              # tracker + evaluator kernels of this handle
     trk.check()
-    kernel_ms = float(np.mean([x.elapsed_time(y) for x, y in kev]))
+    kernel_ms = float(np.mean([x.elapsed_time(y) for x, y, _ in kev]))
+    eval_ms = float(np.mean([y.elapsed_time(z) for _, y, z in kev]))      # report count + PCP / MPJPE counters
     gather_ms = pdist.max_over_ranks(float(np.mean([x.elapsed_time(y) for x, y in gather_ev])), dev) if gather_ev else None
     reports = int(out["count"].sum().item())
     total_frames = (a.sequences_total if strong else world * S) * T
@@ -742,7 +745,8 @@ def main():
                    "gen_seconds": round(gen_s, 1), "cpus_bound_per_rank": numa_cpus, "reports_per_step": int(counters[0].item()),
                    "pcp_percent": (round(100.0 * counters[2].item() / max(1, counters[3].item()), 3) if do_eval else None),
                    "mpjpe_mm": (round(counters[4].item() / max(1, counters[5].item()) / 1e3, 3) if do_eval else None),
-                   "launch": launch_info, "gather_ms_per_step": gather_ms},
+                   "launch": launch_info, "gather_ms_per_step": gather_ms,
+                   "tracker_ms_per_step": kernel_ms, "counters_ms_per_step": eval_ms},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "parity_sample": parity, "single_stream": single, "config5_strong_1024": config5, "other_configs": others,
         "per_frame_api": perframe,
