@@ -607,6 +607,32 @@ __device__ __forceinline__ double dist3(const double* a, const double* b) {
     const double x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
     return sqrt(x * x + y * y + z * z);
 }
+// The same with the short inline square root (MUFU seed, two Newton steps, residual correction: faithfully rounded,
+// no call and no slow-path branch), so that the 26 independent distances of one pose interleave instead of running
+// one after the other (k_eval_pcp is bound by exactly that latency).  A limb test would need `<=` to hold within one
+// ulp to see the difference.
+__device__ __forceinline__ double dist3_inline(const double* a, const double* b) {
+    const double x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
+    return sqrt_f64(x * x + y * y + z * z);
+}
+// joint j of to_shelf14's mapping, alone (same expressions, so the same bits)
+__device__ __forceinline__ void shelf14_joint(const float* __restrict__ p, int remap, int j, double* o) {
+    if (!remap) {
+        for (int k = 0; k < 3; ++k) o[k] = (double)p[j * 3 + k];
+        return;
+    }
+    // {16, 14, 12, 11, 13, 15, 10, 8, 6, 5, 7, 9} packed in nibbles - 5 (no local array, no constant bank)
+    const int m = 5 + (int)((0xB9768A531024ull >> (4 * (11 - j))) & 15ull);
+    if (j < 12) {
+        for (int k = 0; k < 3; ++k) o[k] = (double)p[m * 3 + k];
+        return;
+    }
+    const double top[3] = {0.78, 0.5, 1.5}, bot[3] = {0.3, 0.4, 0.6};
+    for (int k = 0; k < 3; ++k) {
+        const double mid = ((double)p[6 * 3 + k] + (double)p[5 * 3 + k]) / 2.0, nose = (double)p[k];
+        o[k] = mid + (nose - mid) * (j == 13 ? top[k] : bot[k]);
+    }
+}
 #define PAM_EVAL_MAX_P 64
 #define PAM_EVAL_THREADS 128
 #define PAM_EVAL_GT_STRIDE 43      // doubles per staged ground-truth pose (42 + 1: odd stride, no bank conflicts)
@@ -616,7 +642,8 @@ __device__ __forceinline__ double dist3(const double* a, const double* b) {
 // arithmetic then runs out of shared memory.
 __host__ __device__ inline int eval_frames_per_block(int P) { return (PAM_EVAL_THREADS + P - 1) / P + 1; }
 __host__ __device__ inline size_t eval_smem_bytes(int P, int MT, int J) {
-    return (size_t)PAM_EVAL_THREADS * PAM_EVAL_GT_STRIDE * 8 + (size_t)eval_frames_per_block(P) * MT * J * 3 * 4;
+    return (size_t)PAM_EVAL_THREADS * PAM_EVAL_GT_STRIDE * 8 + ((size_t)eval_frames_per_block(P) * MT * J * 3 * 4 + 15) / 16 * 16 +
+           (size_t)P * 20 * 4;          // + the block's counters: 72 KB for the Shelf shape, three blocks per SM
 }
 __global__ void __launch_bounds__(PAM_EVAL_THREADS)
 k_eval_pcp(const int* __restrict__ count, const float* __restrict__ joints, const double* __restrict__ gt,
@@ -626,7 +653,7 @@ k_eval_pcp(const int* __restrict__ count, const float* __restrict__ joints, cons
     double* s_gt = (double*)eval_smem;
     float* s_pred = (float*)(s_gt + PAM_EVAL_THREADS * PAM_EVAL_GT_STRIDE);
     // block-local counters first (shared-memory atomics), one global atomic per counter per block
-    __shared__ unsigned int s_cnt[PAM_EVAL_MAX_P * 20];
+    unsigned int* s_cnt = (unsigned int*)(eval_smem + eval_smem_bytes(P, MT, J) - (size_t)P * 20 * 4);
     __shared__ double s_err[4];
     __shared__ unsigned int s_nj;
     for (int i = threadIdx.x; i < P * 20; i += blockDim.x) s_cnt[i] = 0u;
@@ -671,29 +698,55 @@ k_eval_pcp(const int* __restrict__ count, const float* __restrict__ joints, cons
             } else {
                 const double* g = s_gt + threadIdx.x * PAM_EVAL_GT_STRIDE;
                 const float* pf = s_pred + (int64_t)(st - frame0) * MT * J * 3;
-                double best = 0.0, bm[14][3];
+                // The mapped prediction is never kept whole (42 doubles per thread): joints are re-read from shared
+                // memory where they are needed.  Four candidates are summed side by side (independent chains, each in
+                // the reference's order), and every joint distance is taken once -- the limb tests and the MPJPE sum
+                // use the same 14 values (evalmodel.py:176-200 computes them twice, to the same bits).
+                double best = 0.0;
                 int bq = 0;
-                for (int q = 0; q < k; ++q) {
-                    to_shelf14(pf + q * J * 3, remap, bm);
-                    double d = 0.0;        // vectorize_distance: squared distance over all 42 coordinates
-                    for (int j = 0; j < 14; ++j)
-                        for (int c = 0; c < 3; ++c) { const double x = g[j * 3 + c] - bm[j][c]; d += x * x; }
-                    if (q == 0 || d < best) { best = d; bq = q; }
+                for (int q0 = 0; q0 < k; q0 += 4) {
+                    double d[4] = {0.0, 0.0, 0.0, 0.0};      // vectorize_distance: squared distance over all 42 coordinates
+                    const float* pq[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) pq[u] = pf + (q0 + u < k ? q0 + u : k - 1) * J * 3;
+#pragma unroll 2
+                    for (int j = 0; j < 14; ++j) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            double m[3];
+                            shelf14_joint(pq[u], remap, j, m);
+                            for (int c = 0; c < 3; ++c) { const double x = g[j * 3 + c] - m[c]; d[u] += x * x; }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (q0 + u < k && ((q0 + u) == 0 || d[u] < best)) { best = d[u]; bq = q0 + u; }
                 }
-                to_shelf14(pf + bq * J * 3, remap, bm);      // the closest prediction again (shared memory: cheap)
+                const float* pb = pf + bq * J * 3;           // the closest prediction
+                double dj[14], m2[3], m3[3];
+#pragma unroll
+                for (int j = 0; j < 14; ++j) {
+                    double m[3];
+                    shelf14_joint(pb, remap, j, m);
+                    if (j == 2) { m2[0] = m[0]; m2[1] = m[1]; m2[2] = m[2]; }
+                    if (j == 3) { m3[0] = m[0]; m3[1] = m[1]; m3[2] = m[2]; }
+                    dj[j] = dist3_inline(g + j * 3, m);
+                }
                 const int bones[9][2] = {{0, 1}, {1, 2}, {3, 4}, {4, 5}, {6, 7}, {7, 8}, {9, 10}, {10, 11}, {12, 13}};
+#pragma unroll
                 for (int b = 0; b < 9; ++b) {
                     const int s0 = bones[b][0], e0 = bones[b][1];
-                    const double len = dist3(g + e0 * 3, g + s0 * 3);
-                    if ((dist3(g + s0 * 3, bm[s0]) + dist3(g + e0 * 3, bm[e0])) / 2.0 <= alpha * len) atomicAdd(cnt + b * 2, 1u);
+                    const double len = dist3_inline(g + e0 * 3, g + s0 * 3);
+                    if ((dj[s0] + dj[e0]) / 2.0 <= alpha * len) atomicAdd(cnt + b * 2, 1u);
                     atomicAdd(cnt + b * 2 + 1, 1u);
                 }
                 double gh[3], mh[3];
-                for (int c = 0; c < 3; ++c) { gh[c] = (g[2 * 3 + c] + g[3 * 3 + c]) / 2.0; mh[c] = (bm[2][c] + bm[3][c]) / 2.0; }
-                const double len = dist3(g + 12 * 3, gh);
-                if ((dist3(gh, mh) + dist3(g + 12 * 3, bm[12])) / 2.0 <= alpha * len) atomicAdd(cnt + 18, 1u);
+                for (int c = 0; c < 3; ++c) { gh[c] = (g[2 * 3 + c] + g[3 * 3 + c]) / 2.0; mh[c] = (m2[c] + m3[c]) / 2.0; }
+                const double len = dist3_inline(g + 12 * 3, gh);
+                if ((dist3_inline(gh, mh) + dj[12]) / 2.0 <= alpha * len) atomicAdd(cnt + 18, 1u);
                 atomicAdd(cnt + 19, 1u);
-                for (int j = 0; j < 14; ++j) e += dist3(g + j * 3, bm[j]);
+#pragma unroll
+                for (int j = 0; j < 14; ++j) e += dj[j];
                 scored = true;
             }
         }
