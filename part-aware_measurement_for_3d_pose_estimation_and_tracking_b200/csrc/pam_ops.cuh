@@ -635,7 +635,7 @@ __device__ __forceinline__ void shelf14_joint(const float* __restrict__ p, int r
 }
 #define PAM_EVAL_MAX_P 64
 #define PAM_EVAL_THREADS 128
-#define PAM_EVAL_GT_STRIDE 43      // doubles per staged ground-truth pose (42 + 1: odd stride, no bank conflicts)
+#define PAM_EVAL_GT_STRIDE 42      // doubles per staged ground-truth pose: rows stay contiguous, as in HBM (one bulk copy)
 // Dynamic shared memory: the block's 128 ground-truth poses [128][43] f64, then the predicted poses of the frames
 // they belong to [frames][MT][J][3] f32.  Both are contiguous in HBM, so they are staged with fully coalesced loads
 // (the kernel is bandwidth bound: 1344 B of ground truth + up to MT x J x 12 B of predictions per frame); the
@@ -649,13 +649,14 @@ __global__ void __launch_bounds__(PAM_EVAL_THREADS)
 k_eval_pcp(const int* __restrict__ count, const float* __restrict__ joints, const double* __restrict__ gt,
            const unsigned char* __restrict__ gt_valid, int S, int T, int P, int MT, int J, int remap,
            int t0, int t1, double alpha, unsigned long long* __restrict__ counters, double* __restrict__ mpjpe) {
-    extern __shared__ __align__(16) unsigned char eval_smem[];
+    extern __shared__ __align__(128) unsigned char eval_smem[];
     double* s_gt = (double*)eval_smem;
     float* s_pred = (float*)(s_gt + PAM_EVAL_THREADS * PAM_EVAL_GT_STRIDE);
     // block-local counters first (shared-memory atomics), one global atomic per counter per block
     unsigned int* s_cnt = (unsigned int*)(eval_smem + eval_smem_bytes(P, MT, J) - (size_t)P * 20 * 4);
     __shared__ double s_err[4];
     __shared__ unsigned int s_nj;
+    __shared__ __align__(8) unsigned long long s_bar;
     for (int i = threadIdx.x; i < P * 20; i += blockDim.x) s_cnt[i] = 0u;
     if (threadIdx.x < 4) s_err[threadIdx.x] = 0.0;
     if (threadIdx.x == 0) s_nj = 0u;
@@ -664,12 +665,31 @@ k_eval_pcp(const int* __restrict__ count, const float* __restrict__ joints, cons
     const int nitems = (int)((total - item0) < PAM_EVAL_THREADS ? (total - item0) : PAM_EVAL_THREADS);
     const int64_t frame0 = item0 / P, frame1 = (item0 + nitems - 1) / P;       // flattened (sequence, frame) indices
     const int nframes = (int)(frame1 - frame0 + 1);
-    {   // ground truth: nitems x 42 contiguous doubles -> padded rows
-        const double* src = gt + item0 * 42;
-        for (int i = threadIdx.x; i < nitems * 42; i += PAM_EVAL_THREADS) {
-            const int r = i / 42, e = i - r * 42;
-            s_gt[r * PAM_EVAL_GT_STRIDE + e] = src[i];
-        }
+    // this thread's item: its scalar inputs are requested before the staging barrier, their latency overlaps the copies
+    const int64_t it = item0 + threadIdx.x;
+    const int local = (int)(item0 - frame0 * P) + (int)threadIdx.x;            // item index relative to the block's first frame
+    const int df = local / P, pid = local - df * P;
+    const int64_t st = frame0 + df;
+    int t = (int)(frame0 % T) + df;
+    while (t >= T) t -= T;
+    const bool live = it < total && t >= t0 && t < t1;
+    const bool valid = live && gt_valid[it];
+    const int cnt_st = live ? count[st] : 0;
+    const double* src = gt + item0 * 42;
+    const bool bulk = (((uintptr_t)src) & 15) == 0;          // 336 B per pose: every block offset is a multiple of 16
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+    if (bulk && threadIdx.x == 0) {
+        // ground truth: nitems x 42 contiguous doubles, ONE bulk copy through the TMA engine
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_gt), bytes = (unsigned)nitems * 336u;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    }
+    {
+        if (!bulk)
+            for (int i = threadIdx.x; i < nitems * 42; i += PAM_EVAL_THREADS) s_gt[i] = src[i];
         // predictions: nframes x MT x J x 3 contiguous floats
         const int row = MT * J * 3;
         const float* ps = joints + frame0 * row;
@@ -683,16 +703,18 @@ k_eval_pcp(const int* __restrict__ count, const float* __restrict__ joints, cons
         }
     }
     __syncthreads();
-    const int64_t it = item0 + threadIdx.x;
+    if (bulk)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "PAM_EVAL_WAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+            "@!p bra PAM_EVAL_WAIT_%=;\n\t}" ::"r"(bar) : "memory");
     double e = 0.0;
     bool scored = false;
-    if (it < total) {
-        const int pid = (int)(it % P);
-        const int64_t st = it / P;
-        const int t = (int)(st % T);
-        if (t >= t0 && t < t1 && gt_valid[it]) {
+    {
+        if (valid) {
             unsigned int* cnt = s_cnt + pid * 20;
-            const int k = count[st] < MT ? count[st] : MT;      // rows beyond the output stride were not written
+            const int k = cnt_st < MT ? cnt_st : MT;            // rows beyond the output stride were not written
             if (k <= 0) {                  // "Cannot get any pose in frame": all ten parts count as errors
                 for (int b = 0; b < 10; ++b) atomicAdd(cnt + b * 2 + 1, 1u);
             } else {
