@@ -642,7 +642,8 @@ __device__ __forceinline__ void shelf14_joint(const float* __restrict__ p, int r
 // arithmetic then runs out of shared memory.
 __host__ __device__ inline int eval_frames_per_block(int P) { return (PAM_EVAL_THREADS + P - 1) / P + 1; }
 __host__ __device__ inline size_t eval_smem_bytes(int P, int MT, int J) {
-    return (size_t)PAM_EVAL_THREADS * PAM_EVAL_GT_STRIDE * 8 + ((size_t)eval_frames_per_block(P) * MT * J * 3 * 4 + 15) / 16 * 16 +
+    // (+ 32: the predictions are bulk-copied from the 16-byte boundary below their first byte, in 16-byte units)
+    return (size_t)PAM_EVAL_THREADS * PAM_EVAL_GT_STRIDE * 8 + ((size_t)eval_frames_per_block(P) * MT * J * 3 * 4 + 15) / 16 * 16 + 32 +
            (size_t)P * 20 * 4;          // + the block's counters: 72 KB for the Shelf shape, three blocks per SM
 }
 __global__ void __launch_bounds__(PAM_EVAL_THREADS)
@@ -651,7 +652,7 @@ k_eval_pcp(const int* __restrict__ count, const float* __restrict__ joints, cons
            int t0, int t1, double alpha, unsigned long long* __restrict__ counters, double* __restrict__ mpjpe) {
     extern __shared__ __align__(128) unsigned char eval_smem[];
     double* s_gt = (double*)eval_smem;
-    float* s_pred = (float*)(s_gt + PAM_EVAL_THREADS * PAM_EVAL_GT_STRIDE);
+    unsigned char* s_pred_raw = (unsigned char*)(s_gt + PAM_EVAL_THREADS * PAM_EVAL_GT_STRIDE);      // 16-byte aligned
     // block-local counters first (shared-memory atomics), one global atomic per counter per block
     unsigned int* s_cnt = (unsigned int*)(eval_smem + eval_smem_bytes(P, MT, J) - (size_t)P * 20 * 4);
     __shared__ double s_err[4];
@@ -676,31 +677,32 @@ k_eval_pcp(const int* __restrict__ count, const float* __restrict__ joints, cons
     const bool valid = live && gt_valid[it];
     const int cnt_st = live ? count[st] : 0;
     const double* src = gt + item0 * 42;
-    const bool bulk = (((uintptr_t)src) & 15) == 0;          // 336 B per pose: every block offset is a multiple of 16
+    // predictions of the block's frames: nframes x MT x J x 3 contiguous floats, starting anywhere on a 4-byte boundary
+    const int row = MT * J * 3;
+    const float* ps = joints + frame0 * row;
+    const int n = nframes * row;
+    const unsigned mis = (unsigned)(((uintptr_t)ps) & 15);
+    float* s_pred = (float*)(s_pred_raw + mis);
+    // Bulk copies (TMA): the ground truth as it is (336 B per pose: every block offset is a multiple of 16), the
+    // predictions from the 16-byte boundary below their first byte, rounded up to 16-byte units -- except in the last
+    // block, where that could read past the end of the tensor.
+    const bool bulk = (((uintptr_t)src) & 15) == 0 && blockIdx.x + 1 < gridDim.x;
     const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
     if (bulk && threadIdx.x == 0) {
-        // ground truth: nitems x 42 contiguous doubles, ONE bulk copy through the TMA engine
         const unsigned dst = (unsigned)__cvta_generic_to_shared(s_gt), bytes = (unsigned)nitems * 336u;
+        const unsigned pdst = (unsigned)__cvta_generic_to_shared(s_pred_raw), pbytes = ((unsigned)n * 4u + mis + 15u) & ~15u;
+        const unsigned char* psrc = (const unsigned char*)ps - mis;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes + pbytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(pdst), "l"(psrc), "r"(pbytes), "r"(bar) : "memory");
     }
-    {
-        if (!bulk)
-            for (int i = threadIdx.x; i < nitems * 42; i += PAM_EVAL_THREADS) s_gt[i] = src[i];
-        // predictions: nframes x MT x J x 3 contiguous floats
-        const int row = MT * J * 3;
-        const float* ps = joints + frame0 * row;
-        const int n = nframes * row;
-        if ((((uintptr_t)ps) & 15) == 0 && (n & 3) == 0) {
-            const float4* p4 = (const float4*)ps;
-            float4* d4 = (float4*)s_pred;
-            for (int i = threadIdx.x; i < n / 4; i += PAM_EVAL_THREADS) d4[i] = p4[i];
-        } else {
-            for (int i = threadIdx.x; i < n; i += PAM_EVAL_THREADS) s_pred[i] = ps[i];
-        }
+    if (!bulk) {
+        for (int i = threadIdx.x; i < nitems * 42; i += PAM_EVAL_THREADS) s_gt[i] = src[i];
+        for (int i = threadIdx.x; i < n; i += PAM_EVAL_THREADS) s_pred[i] = ps[i];
     }
     __syncthreads();
     if (bulk)
