@@ -587,6 +587,9 @@ PAM_HD bool track_reported(const DevCfg& c, const Seq<K>& sq, int i) {
 // `hook.dets_released()` is called by every thread once the staged detections are no longer needed
 // (single-buffered launches start the copy of the next frame there).
 // The caller must synchronise the group after frame_step returns.
+// two assignments whose totals agree to this relative width are left to the general solver (2^-40)
+#define PAM_ASSIGN_TIE 9.094947017729282e-13
+
 // index of the k-th set bit of m (k < popcount(m))
 PAM_HD int nth_set_bit(uint32_t m, int k) {
     PAM_NOUNROLL for (; k > 0; --k) m &= m - 1u;
@@ -602,7 +605,7 @@ PAM_HD int nth_set_bit(uint32_t m, int k) {
 // (candidates with the same positive pairs have bit-identical totals), the threads keep their best candidate and two
 // shared-memory atomics pick the largest total.  The solver of the reference reaches the same optimum unless two
 // different matchings tie to within rounding.  Returns false (nothing written) when the problem has more than `limit`
-// candidates or when two different matchings tie exactly: the caller then runs the general solver.
+// candidates or when two different matchings tie to within 2^-40: the caller then runs the general solver.
 template <class Ctx, class K>
 PAM_HD bool assign_enumerated(Ctx& ctx, SeqShared<K>& sh, int cam, int n, int mm, int limit) {
     const double (*A)[K::D] = sh.aff[cam];
@@ -655,19 +658,28 @@ PAM_HD bool assign_enumerated(Ctx& ctx, SeqShared<K>& sh, int cam, int n, int mm
     }
     if (best >= 0.0) ctx.atomic_max_u64(&fs.bf_best, bits_of(best));
     ctx.sync();
-    // the candidates that reach the maximum: lowest index, and whether they all hold the same positive pairs
-    if (best >= 0.0 && bits_of(best) == fs.bf_best) {
-        PAM_FOR(k, P) {
-            unsigned long long sig;
-            if (bits_of(total(k, sig)) != fs.bf_best) continue;
-            ctx.atomic_min(&fs.bf_k, k);
-            ctx.atomic_min_u64(&fs.bf_sig_lo, sig);
-            ctx.atomic_max_u64(&fs.bf_sig_hi, sig);
+    // the candidates within 2^-40 of the maximum (the totals of two matchings that tie in exact arithmetic can differ in
+    // the last bits, their terms being added in different orders): lowest index among those that reach it, and whether
+    // they all hold the same positive pairs
+    {
+        double top;
+        const unsigned long long tb = fs.bf_best;
+        memcpy(&top, &tb, 8);
+        const double near_top = top * (1.0 - PAM_ASSIGN_TIE);
+        if (best >= near_top) {
+            PAM_FOR(k, P) {
+                unsigned long long sig;
+                const double t = total(k, sig);
+                if (!(t >= near_top)) continue;
+                if (bits_of(t) == tb) ctx.atomic_min(&fs.bf_k, k);
+                ctx.atomic_min_u64(&fs.bf_sig_lo, sig);
+                ctx.atomic_max_u64(&fs.bf_sig_hi, sig);
+            }
         }
     }
     ctx.sync();
-    // two different matchings with the same total (duplicated detections or tracks): which one the reference's solver
-    // returns depends on its pivoting order, so that solver decides
+    // two different matchings with (nearly) the same total -- duplicated detections or tracks: which one the
+    // reference's solver returns depends on its pivoting order and its own rounding, so that solver decides
     if (fs.bf_sig_lo != fs.bf_sig_hi) return false;
     if (ctx.tid() == 0) {
         int k = fs.bf_k;
@@ -688,7 +700,7 @@ PAM_HD bool assign_enumerated(Ctx& ctx, SeqShared<K>& sh, int cam, int n, int mm
 // The same problem when, besides the pairs fixed by the quick test, at most two tracks and two detections -- or one
 // track / one detection against several -- hold positive entries: the rule when two people cross.  One thread
 // decides it in closed form (every camera in parallel).  Returns false when the camera needs more than that, or when
-// the two alternatives tie exactly.
+// the alternatives tie to within 2^-40.
 template <class K>
 PAM_HD bool assign_closed_form(SeqShared<K>& sh, int cam, int n, int mm) {
     const double (*A)[K::D] = sh.aff[cam];
@@ -707,22 +719,23 @@ PAM_HD bool assign_closed_form(SeqShared<K>& sh, int cam, int n, int mm) {
         const bool one_row = r == 1;
         const int fixed = ctz32(one_row ? rows : cols);
         uint32_t rest = one_row ? cols : rows;
-        double best = 0.0;
-        int arg = -1, ties = 0;
+        double best = 0.0, second = 0.0;
+        int arg = -1;
         PAM_NOUNROLL for (; rest; rest &= rest - 1u) {
             const int x = ctz32(rest);
             const double a = one_row ? A[fixed][x] : A[x][fixed];
-            if (a > best) { best = a; arg = x; ties = 0; }
-            else if (a == best) ++ties;
+            if (a > best) { second = best; best = a; arg = x; }
+            else if (a > second) second = a;
         }
-        if (ties || arg < 0) return false;
+        if (arg < 0 || second >= best * (1.0 - PAM_ASSIGN_TIE)) return false;     // (near) tie: the general solver decides
         if (one_row) take(fixed, arg); else take(arg, fixed);
         return true;
     }
     if (r == 2 && cc == 2) {
         const int i0 = ctz32(rows), i1 = ctz32(rows & (rows - 1u)), d0 = ctz32(cols), d1 = ctz32(cols & (cols - 1u));
         const double straight = A[i0][d0] + A[i1][d1], crossed = A[i0][d1] + A[i1][d0];
-        if (straight == crossed) return false;
+        const double hi = straight > crossed ? straight : crossed, lo = straight > crossed ? crossed : straight;
+        if (lo >= hi * (1.0 - PAM_ASSIGN_TIE)) return false;                      // (near) tie: the general solver decides
         if (straight > crossed) { take(i0, d0); take(i1, d1); }
         else { take(i0, d1); take(i1, d0); }
         return true;

@@ -110,6 +110,45 @@ extern "C" double hostemu_sqrt(double x) { return pam::sqrt_f64(x); }
 extern "C" double hostemu_rsqrt(double x) { return pam::rsqrt_f64(x); }
 extern "C" double hostemu_rcp(double x) { return pam::rcp_f64(x); }
 
+// One camera's assignment problem through the kernel's own solvers (pam_track.h: quick test as in phase 3 of
+// frame_step, then assign_closed_form, assign_enumerated, and the general solver when those decline).
+// A [n][mm] affinities (n <= 32 tracks, mm <= 16 detections); t2d [n] = detection of each track or -1;
+// returns which stage decided: 0 quick test, 1 closed form, 2 enumeration, 3 general solver.
+extern "C" int hostemu_assign(const double* A, int n, int mm, int limit, int* t2d) {
+    typedef pam::CapsMax K;
+    static pam::SeqShared<K> sh;
+    memset(&sh, 0, sizeof sh);
+    memset(sh.match, -1, sizeof sh.match);
+    for (int i = 0; i < n; ++i) for (int d = 0; d < mm; ++d) sh.aff[0][i][d] = A[i * mm + d];
+    sh.m[0] = (signed char)mm;
+    bool conflict = false;
+    for (int i = 0; i < n; ++i) {                       // the quick test of phase 3
+        int cnt = 0, arg = -1;
+        for (int d = 0; d < mm; ++d) if (sh.aff[0][i][d] > 0.0) { ++cnt; arg = d; }
+        if (cnt == 1) {
+            int col = 0;
+            for (int k = 0; k < n; ++k) col += (sh.aff[0][k][arg] > 0.0) ? 1 : 0;
+            if (col == 1) { sh.t2d(0, i) = (signed char)arg; sh.d2t(0, arg) = (signed char)i; }
+            else conflict = true;
+        } else if (cnt > 1) conflict = true;
+    }
+    int how = 0;
+    if (conflict) {
+        pam::HostCtx ctx;
+        if (pam::assign_closed_form(sh, 0, n, mm)) how = 1;
+        else if (pam::assign_enumerated(ctx, sh, 0, n, mm, limit)) how = 2;
+        else {
+            how = 3;
+            for (int i = 0; i < n; ++i) sh.t2d(0, i) = -1;
+            int col4row[PAM_LSAP_N];
+            pam::lsap_solve<PAM_LSAP_N>(n, mm, [&](int i, int d) { return -sh.aff[0][i][d]; }, col4row);
+            for (int i = 0; i < n; ++i) if (col4row[i] >= 0 && sh.aff[0][i][col4row[i]] > 0.0) sh.t2d(0, i) = (signed char)col4row[i];
+        }
+    }
+    for (int i = 0; i < n; ++i) t2d[i] = sh.t2d(0, i);
+    return how;
+}
+
 // DLT extractor check: n joints, V views each; mode 0 = product policy (Gram when all weights are 1),
 // 1 = force Givens + inverse iteration/Jacobi, 2 = force Givens + Jacobi only.
 extern "C" int hostemu_dlt(int n, int V, const double* P, const double* uv, const double* w, const uint8_t* keep,

@@ -136,3 +136,47 @@ def test_mean_confidence_is_get_believe(lib):
                 assert np.isnan(got)
             else:
                 assert got == float(np.mean(sel)), (J, neg)
+
+
+def test_small_assignment_solvers_agree_with_scipy(lib):
+    """The kernel's closed-form and enumerated assignment (csrc/pam_track.h: assign_closed_form, assign_enumerated) on
+    random sparse affinity matrices: the matched (track, detection) pairs with positive affinity are those of
+    scipy.optimize.linear_sum_assignment(-A) (IterativeTracker.py:150-160).  Exact ties between different matchings
+    (duplicated columns / rows) must be handed to the general solver, which follows scipy's order."""
+    from scipy.optimize import linear_sum_assignment
+    rng = np.random.default_rng(5)
+    stages = {0: 0, 1: 0, 2: 0, 3: 0}
+
+    def check(A, limit=1024):
+        n, mm = A.shape
+        t2d = np.zeros(n, np.int32)
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        how = lib.hostemu_assign(A.ctypes.data_as(C.c_void_p), n, mm, limit, t2d.ctypes.data_as(C.c_void_p))
+        stages[how] += 1
+        rows, cols = linear_sum_assignment(-A)
+        want = np.full(n, -1, np.int32)
+        for r, c in zip(rows, cols):
+            if A[r, c] > 0:
+                want[r] = c
+        assert np.array_equal(t2d, want), (how, A, t2d, want)
+        return how
+
+    for trial in range(4000):
+        n, mm = int(rng.integers(1, 9)), int(rng.integers(1, 7))
+        A = rng.uniform(0.05, 1.0, (n, mm)) * (rng.random((n, mm)) < rng.choice([0.15, 0.3, 0.6]))
+        check(A)
+    for trial in range(300):                                   # larger problems: enumeration limit, then the general solver
+        n, mm = int(rng.integers(6, 20)), int(rng.integers(5, 14))
+        A = rng.uniform(0.05, 1.0, (n, mm)) * (rng.random((n, mm)) < 0.5)
+        check(A, limit=int(rng.choice([32, 1024, 4096])))
+    # structural ties: two identical detections / two identical tracks -> general solver (scipy's pivoting order)
+    for trial in range(300):
+        n, mm = int(rng.integers(2, 7)), int(rng.integers(2, 6))
+        A = rng.uniform(0.05, 1.0, (n, mm)) * (rng.random((n, mm)) < 0.7)
+        if trial % 2:
+            A[:, -1] = A[:, 0]
+        else:
+            A[-1, :] = A[0, :]
+        check(A)
+    assert all(v > 0 for v in stages.values()), stages
+    print("assignment stages used (quick, closed form, enumeration, general):", stages)
